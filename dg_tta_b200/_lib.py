@@ -1,0 +1,76 @@
+"""ctypes binding of libdgtta_sm100.so (C ABI declared in include/dgtta.h).
+
+There is deliberately no fallback: if the CUDA library is missing or fails to load, every
+operator of this package raises.  The oracle under oracle/ is test infrastructure and is never
+imported from here.
+"""
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdgtta_sm100.so"
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/dgtta.h one to one (checked by tests/test_abi_symbols.py)
+SIGNATURES = {
+    "dgtta_abi_version": (c_int, []),
+    "dgtta_last_error": (c_char_p, []),
+    "dgtta_mind_workspace_bytes": (c_size_t, [c_int] * 4),
+    "dgtta_mind_ssc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                   c_float, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
+    "dgtta_mind_philox_offset_increment": (c_uint64, [c_int] * 6),
+    "dgtta_gin_workspace_bytes": (c_size_t, [c_int] * 7),
+    "dgtta_gin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dgtta_gin_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "dgtta_affine_sample_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "dgtta_affine_sample_bwd_input": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+}
+
+
+class DgttaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built (python -m dg_tta_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise DgttaError(
+                f"{LIB_PATH} is missing: build it with `python -m dg_tta_b200.build` "
+                "(nvcc, sm_100a).  dg_tta_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name, None)
+            if fn is None:
+                continue  # optional symbols are checked where they are used
+            fn.restype = res
+            fn.argtypes = args
+        if handle.dgtta_abi_version() != 1:
+            raise DgttaError("libdgtta_sm100.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dgtta_last_error()
+        raise DgttaError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda_f32(t, name):
+    """Boundary contract: CUDA, float32; made contiguous by the caller."""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must live on a CUDA device: dg_tta_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")

@@ -1,0 +1,212 @@
+// Affine view warp: F.affine_grid + F.grid_sample fused into one gather (forward) / scatter (adjoint).
+//
+// Replaces the op pairs at dg_tta/tta/tta.py:523-532+548-551 (image warp, border padding),
+// tta.py:571-575 (inverse warp of the prediction, zeros padding, autograd w.r.t. the input) and
+// dg_tta/tta/torch_utils.py:55-73 (patch crop; nearest for labels).  align_corners=False throughout.
+// Coordinates follow torch (third party; ATen/native/AffineGridGenerator.cpp, GridSampler.h):
+//     base_i = linspace(-1, 1, N)[i] * (N-1) / N          (linspace evaluated from both ends)
+//     (gx,gy,gz) = theta[b] . (base_w, base_h, base_d, 1)
+//     ix = ((gx + 1) * W_in - 1) / 2 ; border: clamp to [0, W_in-1] ; zeros: corners outside contribute 0
+// No grid tensor is ever materialised (the reference builds three 12 B/voxel grids per warp).
+#include "common.cuh"
+
+namespace dgtta {
+
+struct SampleParams {
+    const float *in;
+    const float *theta;
+    float *out;
+    int B, C, Di, Hi, Wi, Do, Ho, Wo;
+};
+
+__device__ __forceinline__ float base_coord(int i, int n)
+{
+    if (n <= 1) return 0.f;
+    const float step = __fdiv_rn(2.f, (float)(n - 1));
+    const float v = (i < n / 2) ? __fadd_rn(-1.f, __fmul_rn(step, (float)i))
+                                : __fsub_rn(1.f, __fmul_rn(step, (float)(n - 1 - i)));
+    return __fdiv_rn(__fmul_rn(v, (float)(n - 1)), (float)n);
+}
+
+__device__ __forceinline__ float unnormalize(float g, int size)
+{
+    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 0.5f);
+}
+
+__device__ __forceinline__ float clip_coord(float v, int size) { return fminf(fmaxf(v, 0.f), (float)(size - 1)); }
+
+struct Coords {
+    float ix, iy, iz;
+};
+
+template <int PAD>
+__device__ __forceinline__ Coords source_coords(const SampleParams &P, const float *th, int d, int h, int w)
+{
+    const float xn = base_coord(w, P.Wo), yn = base_coord(h, P.Ho), zn = base_coord(d, P.Do);
+    // row-times-column products summed left to right, like the reference's base_grid @ theta^T
+    const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[0], xn), __fmul_rn(th[1], yn)), __fmul_rn(th[2], zn)), th[3]);
+    const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[4], xn), __fmul_rn(th[5], yn)), __fmul_rn(th[6], zn)), th[7]);
+    const float gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[8], xn), __fmul_rn(th[9], yn)), __fmul_rn(th[10], zn)), th[11]);
+    Coords c;
+    c.ix = unnormalize(gx, P.Wi); c.iy = unnormalize(gy, P.Hi); c.iz = unnormalize(gz, P.Di);
+    if (PAD == DGTTA_PAD_BORDER) { c.ix = clip_coord(c.ix, P.Wi); c.iy = clip_coord(c.iy, P.Hi); c.iz = clip_coord(c.iz, P.Di); }
+    return c;
+}
+
+constexpr int SAMPLE_THREADS = 256;
+
+// one thread per output voxel; channels looped inside so coordinates and weights are computed once
+template <int INTERP, int PAD>
+__global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const __grid_constant__ SampleParams P)
+{
+    const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
+    const int b = blockIdx.y;
+    __shared__ float th[12];
+    if (threadIdx.x < 12) th[threadIdx.x] = P.theta[b * 12 + threadIdx.x];
+    __syncthreads();
+    for (size_t p = (size_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x; p < Vo; p += (size_t)gridDim.x * SAMPLE_THREADS) {
+        const int w = (int)(p % P.Wo);
+        const int h = (int)((p / P.Wo) % P.Ho);
+        const int d = (int)(p / ((size_t)P.Wo * P.Ho));
+        const Coords c = source_coords<PAD>(P, th, d, h, w);
+        const float *src = P.in + (size_t)b * P.C * Vi;
+        float *dst = P.out + (size_t)b * P.C * Vo + p;
+        if (INTERP == DGTTA_INTERP_NEAREST) {
+            const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
+            const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
+            const size_t off = ok ? ((size_t)(int)rz * P.Hi + (int)ry) * P.Wi + (int)rx : 0;
+            for (int ch = 0; ch < P.C; ++ch) __stcs(dst + ch * Vo, ok ? __ldg(src + ch * Vi + off) : 0.f);
+        } else {
+            const float fx = floorf(c.ix), fy = floorf(c.iy), fz = floorf(c.iz);
+            const float tx = c.ix - fx, ty = c.iy - fy, tz = c.iz - fz;
+            // clamp before the int conversion so that wild coordinates cannot overflow
+            const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)P.Wi), y0 = (int)fminf(fmaxf(fy, -2.f), (float)P.Hi),
+                      z0 = (int)fminf(fmaxf(fz, -2.f), (float)P.Di);
+            float wgt[8];
+            int off[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+                const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+                const bool ok = xx >= 0 && xx < P.Wi && yy >= 0 && yy < P.Hi && zz >= 0 && zz < P.Di;
+                const float wv = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+                wgt[k] = ok ? wv : 0.f;
+                off[k] = ok ? (zz * P.Hi + yy) * P.Wi + xx : 0;
+            }
+            for (int ch = 0; ch < P.C; ++ch) {
+                const float *s = src + ch * Vi;
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(s + off[k]), wgt[k], acc);
+                __stcs(dst + ch * Vo, acc);
+            }
+        }
+    }
+}
+
+// adjoint of the trilinear forward: scatter grad_out into grad_in (pre-zeroed) with red.global.add
+template <int PAD>
+__global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const __grid_constant__ SampleParams P)
+{
+    // here P.in = grad_out [B,C,Do,Ho,Wo], P.out = grad_in [B,C,Di,Hi,Wi]
+    const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
+    const int b = blockIdx.y;
+    __shared__ float th[12];
+    if (threadIdx.x < 12) th[threadIdx.x] = P.theta[b * 12 + threadIdx.x];
+    __syncthreads();
+    for (size_t p = (size_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x; p < Vo; p += (size_t)gridDim.x * SAMPLE_THREADS) {
+        const int w = (int)(p % P.Wo);
+        const int h = (int)((p / P.Wo) % P.Ho);
+        const int d = (int)(p / ((size_t)P.Wo * P.Ho));
+        const Coords c = source_coords<PAD>(P, th, d, h, w);
+        const float fx = floorf(c.ix), fy = floorf(c.iy), fz = floorf(c.iz);
+        const float tx = c.ix - fx, ty = c.iy - fy, tz = c.iz - fz;
+        const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)P.Wi), y0 = (int)fminf(fmaxf(fy, -2.f), (float)P.Hi),
+                  z0 = (int)fminf(fmaxf(fz, -2.f), (float)P.Di);
+        float wgt[8];
+        int off[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+            const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+            const bool ok = xx >= 0 && xx < P.Wi && yy >= 0 && yy < P.Hi && zz >= 0 && zz < P.Di;
+            wgt[k] = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+            off[k] = ok ? (zz * P.Hi + yy) * P.Wi + xx : -1;
+        }
+        const float *go = P.in + (size_t)b * P.C * Vo + p;
+        float *gi = P.out + (size_t)b * P.C * Vi;
+        for (int ch = 0; ch < P.C; ++ch) {
+            const float g = __ldg(go + ch * Vo);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (off[k] >= 0) atomicAdd(gi + ch * Vi + off[k], g * wgt[k]);
+        }
+    }
+}
+
+static int sample_check(const void *a, const void *t, const void *o, int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo)
+{
+    if (!a || !t || !o) { set_error("dgtta_affine_sample: null pointer"); return DGTTA_ENULL; }
+    if (B <= 0 || C <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || B > 65535) {
+        set_error("dgtta_affine_sample: bad shape");
+        return DGTTA_EINVAL;
+    }
+    if ((size_t)Di * Hi * Wi >= (size_t)1 << 31 || (size_t)Do * Ho * Wo >= (size_t)1 << 31) {
+        set_error("dgtta_affine_sample: volume too large");
+        return DGTTA_EINVAL;
+    }
+    return 0;
+}
+
+static dim3 sample_grid(size_t Vo, int B)
+{
+    size_t gx = (Vo + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+    const size_t cap = (size_t)sm_count() * 16;  // grid-stride beyond 16 CTAs per SM
+    if (gx > cap) gx = cap;
+    return dim3((unsigned)gx, (unsigned)B, 1);
+}
+
+}  // namespace dgtta
+
+using namespace dgtta;
+
+extern "C" int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_dev, float *out_dev, int B, int C,
+                                       int Di, int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding,
+                                       dgtta_stream_t stream_)
+{
+    int rc = sample_check(in_dev, theta_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo);
+    if (rc) return rc;
+    if ((interp != DGTTA_INTERP_TRILINEAR && interp != DGTTA_INTERP_NEAREST) ||
+        (padding != DGTTA_PAD_ZEROS && padding != DGTTA_PAD_BORDER)) {
+        set_error("dgtta_affine_sample_fwd: bad interp/padding");
+        return DGTTA_EINVAL;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SampleParams P{in_dev, theta_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
+    const dim3 grid = sample_grid((size_t)Do * Ho * Wo, B);
+    if (interp == DGTTA_INTERP_TRILINEAR) {
+        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+        else affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+    } else {
+        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+        else affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+    }
+    return check_launch("affine_sample_fwd_kernel");
+}
+
+extern "C" int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const float *theta_dev, float *grad_in_dev,
+                                             int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                                             int padding, dgtta_stream_t stream_)
+{
+    int rc = sample_check(grad_out_dev, theta_dev, grad_in_dev, B, C, Di, Hi, Wi, Do, Ho, Wo);
+    if (rc) return rc;
+    if (padding != DGTTA_PAD_ZEROS && padding != DGTTA_PAD_BORDER) { set_error("dgtta_affine_sample_bwd_input: bad padding"); return DGTTA_EINVAL; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e = cudaMemsetAsync(grad_in_dev, 0, (size_t)B * C * Di * Hi * Wi * sizeof(float), stream);
+    if (e != cudaSuccess) { set_error("dgtta_affine_sample_bwd_input: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    SampleParams P{grad_out_dev, theta_dev, grad_in_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
+    const dim3 grid = sample_grid((size_t)Do * Ho * Wo, B);
+    if (padding == DGTTA_PAD_ZEROS) affine_sample_bwd_kernel<DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+    else affine_sample_bwd_kernel<DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+    return check_launch("affine_sample_bwd_kernel");
+}

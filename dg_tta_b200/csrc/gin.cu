@@ -1,0 +1,306 @@
+// GIN (global intensity non-linear) augmentation for sm_100a.
+//
+// Replaces GINGroupConv.forward (dg_tta/gin.py:168-230) and GradlessGCReplayNonlinBlock.forward
+// (gin.py:59-122) for 5-D input.  Per sample b (weights differ per sample: grouped conv, groups=B):
+//     y_0 = x ;  y_{L+1} = act_L( conv3d_zero_pad(y_L, ker_L[b]) + shift_L[b] ),  act = leaky_relu(0.01) except last
+//     mixed = alpha_b * y_n + (1 - alpha_b) * x
+//     out   = mixed * (1 / (||mixed_b||_F + 1e-5)) * ||x_b||_F
+//
+// This file holds the general path: one direct-convolution launch per layer (any channel counts up to
+// GIN_MAXC, k in {1,3}), the blend and the sum-of-squares partials fused into the last layer, a
+// one-block-per-sample deterministic reduction, and the final rescale (skipped when the caller takes
+// the two scalars instead — see dgtta.h scale_out_dev).
+#include "common.cuh"
+
+namespace dgtta {
+
+constexpr int GIN_MAXC = 8;
+constexpr int GIN_BX = 32, GIN_BY = 8;
+constexpr int GIN_RED_BLOCKS = 1024;  // partial-sum slots per sample
+
+struct GinLayerParams {
+    const float *in;      // [B,cin,D,H,W]
+    float *out;           // [B,cout,D,H,W]
+    const float *wts;     // device copy of this layer's ker [cout*B,cin,k^3] followed by shift [cout*B]
+    const float *x0;      // last layer: the original input (cin0 == cout)
+    const float *alphas;  // last layer: [B]
+    double *partials;     // last layer: [B][GIN_RED_BLOCKS][2]
+    int B, cin, cout, D, H, W;
+    int act, last;
+};
+
+template <int K>
+__global__ void __launch_bounds__(GIN_BX *GIN_BY) gin_layer_kernel(const __grid_constant__ GinLayerParams P)
+{
+    constexpr int K3 = K * K * K, RAD = K / 2;
+    __shared__ float w_s[GIN_MAXC * GIN_MAXC * K3 + GIN_MAXC];
+    __shared__ double red[2][GIN_BX * GIN_BY / 32];
+    const int D = P.D, H = P.H, W = P.W, cin = P.cin, cout = P.cout;
+    const int b = blockIdx.z / D, d = blockIdx.z - b * D;
+    const int tid = threadIdx.y * GIN_BX + threadIdx.x;
+    const int nw = cout * cin * K3;
+    for (int i = tid; i < nw; i += GIN_BX * GIN_BY) w_s[i] = P.wts[(size_t)b * nw + i];
+    float *shift_s = w_s + nw;
+    if (tid < cout) shift_s[tid] = P.wts[(size_t)P.B * nw + b * cout + tid];
+    __syncthreads();
+
+    const int w = blockIdx.x * GIN_BX + threadIdx.x, h = blockIdx.y * GIN_BY + threadIdx.y;
+    const size_t V = (size_t)D * H * W;
+    double s_in = 0.0, s_mix = 0.0;
+    if (w < W && h < H) {
+        float acc[GIN_MAXC];
+#pragma unroll
+        for (int o = 0; o < GIN_MAXC; ++o) acc[o] = 0.f;
+        for (int ic = 0; ic < cin; ++ic) {
+            const float *src = P.in + ((size_t)b * cin + ic) * V;
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                const int dd = d + a - RAD;
+#pragma unroll
+                for (int bq = 0; bq < K; ++bq) {
+                    const int hh = h + bq - RAD;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) {
+                        const int ww = w + c - RAD;
+                        float v = 0.f;  // zero padding (gin.py:105-107)
+                        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                            v = __ldg(src + ((size_t)dd * H + hh) * W + ww);
+                        const int t = (a * K + bq) * K + c;
+#pragma unroll
+                        for (int o = 0; o < GIN_MAXC; ++o)
+                            if (o < cout) acc[o] = fmaf(w_s[(o * cin + ic) * K3 + t], v, acc[o]);
+                    }
+                }
+            }
+        }
+        const size_t p = ((size_t)d * H + h) * W + w;
+#pragma unroll
+        for (int o = 0; o < GIN_MAXC; ++o) {
+            if (o < cout) {
+                float y = acc[o] + shift_s[o];                 // gin.py:111
+                if (P.act) y = y > 0.f ? y : y * 0.01f;       // gin.py:112-113
+                if (P.last) {
+                    const float xin = __ldg(P.x0 + ((size_t)b * cout + o) * V + p);
+                    const float al = __ldg(P.alphas + b);
+                    y = __fadd_rn(__fmul_rn(al, y), __fmul_rn(1.0f - al, xin));  // gin.py:197
+                    s_in += (double)xin * (double)xin;
+                    s_mix += (double)y * (double)y;
+                }
+                P.out[((size_t)b * cout + o) * V + p] = y;
+            }
+        }
+    }
+    if (P.last) {
+        s_in = warp_sum(s_in);
+        s_mix = warp_sum(s_mix);
+        if ((tid & 31) == 0) { red[0][tid >> 5] = s_in; red[1][tid >> 5] = s_mix; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, m = 0.0;
+            for (int i = 0; i < GIN_BX * GIN_BY / 32; ++i) { a += red[0][i]; m += red[1][i]; }
+            // fixed slot per block; several blocks may share a slot -> atomics on doubles.  The final
+            // value is rounded to float after a sqrt, so the addition order is immaterial at fp32.
+            const int slot = ((blockIdx.z - b * D) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) % GIN_RED_BLOCKS;
+            atomicAdd(&P.partials[((size_t)b * GIN_RED_BLOCKS + slot) * 2], a);
+            atomicAdd(&P.partials[((size_t)b * GIN_RED_BLOCKS + slot) * 2 + 1], m);
+        }
+    }
+}
+
+// one block per sample: scale[b] = {1/(||mixed_b||+1e-5), ||x_b||}   (gin.py:200-228)
+__global__ void gin_norm_kernel(const double *partials, float *scale)
+{
+    __shared__ double red[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    double a = 0.0, m = 0.0;
+    for (int i = tid; i < GIN_RED_BLOCKS; i += 256) {
+        a += partials[((size_t)b * GIN_RED_BLOCKS + i) * 2];
+        m += partials[((size_t)b * GIN_RED_BLOCKS + i) * 2 + 1];
+    }
+    a = warp_sum(a); m = warp_sum(m);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = m; }
+    __syncthreads();
+    if (tid == 0) {
+        a = 0.0; m = 0.0;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; m += red[1][i]; }
+        const float in_frob = (float)sqrt(a), self_frob = (float)sqrt(m);
+        scale[2 * b] = __fdiv_rn(1.0f, self_frob + 1e-5f);
+        scale[2 * b + 1] = in_frob;
+    }
+}
+
+// out = (out * scale[b][0]) * scale[b][1], vectorised where aligned
+__global__ void __launch_bounds__(256) gin_scale_kernel(float *out, const float *scale, size_t per_sample)
+{
+    const int b = blockIdx.y;
+    const float s0 = scale[2 * b], s1 = scale[2 * b + 1];
+    float *o = out + (size_t)b * per_sample;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)o) & 15) == 0) {
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        const size_t n4 = per_sample / 4;
+        for (size_t k = i; k < n4; k += stride) {
+            float4 v = o4[k];
+            v.x = __fmul_rn(__fmul_rn(v.x, s0), s1); v.y = __fmul_rn(__fmul_rn(v.y, s0), s1);
+            v.z = __fmul_rn(__fmul_rn(v.z, s0), s1); v.w = __fmul_rn(__fmul_rn(v.w, s0), s1);
+            o4[k] = v;
+        }
+        for (size_t k = n4 * 4 + i; k < per_sample; k += stride) o[k] = __fmul_rn(__fmul_rn(o[k], s0), s1);
+    } else {
+        for (size_t k = i; k < per_sample; k += stride) o[k] = __fmul_rn(__fmul_rn(o[k], s0), s1);
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GinWorkspace {
+    size_t params_off, partials_off, scale_off, buf0_off, buf1_off, total;
+};
+
+static GinWorkspace gin_workspace(int B, int D, int H, int W, int in_ch, int n_layer, int interm)
+{
+    GinWorkspace w;
+    const size_t V = (size_t)D * H * W;
+    size_t nparams = 0;
+    int cin = in_ch;
+    for (int L = 0; L < n_layer; ++L) {
+        const int cout = (L == n_layer - 1) ? in_ch : interm;
+        nparams += (size_t)cout * B * cin * 27 + (size_t)cout * B;  // k=3 upper bound
+        cin = cout;
+    }
+    size_t off = 0;
+    w.params_off = off; off = align_up(off + nparams * sizeof(float), 256);
+    w.partials_off = off; off = align_up(off + (size_t)B * GIN_RED_BLOCKS * 2 * sizeof(double), 256);
+    w.scale_off = off; off = align_up(off + (size_t)B * 2 * sizeof(float), 256);
+    const size_t buf = align_up((size_t)B * interm * V * sizeof(float), 256);
+    w.buf0_off = off; off += buf;
+    w.buf1_off = off; off += buf;
+    w.total = off;
+    return w;
+}
+
+}  // namespace dgtta
+
+using namespace dgtta;
+
+extern "C" size_t dgtta_gin_workspace_bytes(int B, int D, int H, int W, int in_channels, int n_layer, int interm_channels)
+{
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || in_channels <= 0 || n_layer < 2 || interm_channels <= 0) return 0;
+    return gin_workspace(B, D, H, W, in_channels, n_layer, interm_channels).total;
+}
+
+extern "C" int dgtta_gin_fwd(const float *x_dev, float *out_dev, const float *params_host, const int *ksizes_host,
+                             const float *alphas_dev, int B, int D, int H, int W, int in_channels, int n_layer,
+                             int interm_channels, float *scale_out_dev, void *workspace_dev,
+                             size_t workspace_bytes, dgtta_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x_dev || !out_dev || !params_host || !ksizes_host || !alphas_dev || !workspace_dev) {
+        set_error("dgtta_gin_fwd: null pointer");
+        return DGTTA_ENULL;
+    }
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || in_channels <= 0 || n_layer < 2 || interm_channels <= 0) {
+        set_error("dgtta_gin_fwd: bad shape");
+        return DGTTA_EINVAL;
+    }
+    if (in_channels > GIN_MAXC || interm_channels > GIN_MAXC) {
+        set_error("dgtta_gin_fwd: more than %d channels not supported", GIN_MAXC);
+        return DGTTA_EUNSUPPORTED;
+    }
+    if ((size_t)B * D > 65535u || (size_t)D * H * W >= (size_t)1 << 31) { set_error("dgtta_gin_fwd: volume too large"); return DGTTA_EINVAL; }
+    for (int L = 0; L < n_layer; ++L)
+        if (ksizes_host[L] != 1 && ksizes_host[L] != 3) {
+            set_error("dgtta_gin_fwd: kernel size %d (layer %d) not in {1,3}", ksizes_host[L], L);
+            return DGTTA_EINVAL;
+        }
+    const GinWorkspace ws = gin_workspace(B, D, H, W, in_channels, n_layer, interm_channels);
+    if (workspace_bytes < ws.total || ((uintptr_t)workspace_dev & 255)) {
+        set_error("dgtta_gin_fwd: workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, ws.total);
+        return DGTTA_EWORKSPACE;
+    }
+    char *base = (char *)workspace_dev;
+    float *params_dev = (float *)(base + ws.params_off);
+    double *partials = (double *)(base + ws.partials_off);
+    float *scale = scale_out_dev ? scale_out_dev : (float *)(base + ws.scale_off);
+    float *bufs[2] = {(float *)(base + ws.buf0_off), (float *)(base + ws.buf1_off)};
+
+    // actual parameter count for the drawn kernel sizes
+    size_t nparams = 0;
+    {
+        int cin = in_channels;
+        for (int L = 0; L < n_layer; ++L) {
+            const int cout = (L == n_layer - 1) ? in_channels : interm_channels;
+            const int k = ksizes_host[L];
+            nparams += (size_t)cout * B * cin * k * k * k + (size_t)cout * B;
+            cin = cout;
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync(params_dev, params_host, nparams * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { set_error("dgtta_gin_fwd: params upload: %s", cudaGetErrorString(e)); return (int)e; }
+    e = cudaMemsetAsync(partials, 0, (size_t)B * GIN_RED_BLOCKS * 2 * sizeof(double), stream);
+    if (e != cudaSuccess) { set_error("dgtta_gin_fwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+
+    const dim3 block(GIN_BX, GIN_BY, 1);
+    const dim3 grid((W + GIN_BX - 1) / GIN_BX, (H + GIN_BY - 1) / GIN_BY, B * D);
+    const float *cur = x_dev;
+    int cin = in_channels;
+    size_t poff = 0;
+    for (int L = 0; L < n_layer; ++L) {
+        const bool last = L == n_layer - 1;
+        const int cout = last ? in_channels : interm_channels;
+        const int k = ksizes_host[L];
+        GinLayerParams P;
+        P.in = cur;
+        P.out = last ? out_dev : bufs[L & 1];
+        P.wts = params_dev + poff;
+        P.x0 = x_dev; P.alphas = alphas_dev; P.partials = partials;
+        P.B = B; P.cin = cin; P.cout = cout; P.D = D; P.H = H; P.W = W;
+        P.act = last ? 0 : 1; P.last = last ? 1 : 0;
+        if (k == 1) gin_layer_kernel<1><<<grid, block, 0, stream>>>(P);
+        else gin_layer_kernel<3><<<grid, block, 0, stream>>>(P);
+        int rc = check_launch("gin_layer_kernel");
+        if (rc) return rc;
+        poff += (size_t)cout * B * cin * k * k * k + (size_t)cout * B;
+        cur = P.out;
+        cin = cout;
+    }
+    gin_norm_kernel<<<B, 256, 0, stream>>>(partials, scale);
+    int rc = check_launch("gin_norm_kernel");
+    if (rc) return rc;
+    if (!scale_out_dev) {
+        const size_t per_sample = (size_t)in_channels * D * H * W;
+        int gx = (int)((per_sample / 4 + 255) / 256);
+        const int cap = sm_count() * 8;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        gin_scale_kernel<<<dim3(gx, B), 256, 0, stream>>>(out_dev, scale, per_sample);
+        rc = check_launch("gin_scale_kernel");
+    }
+    return rc;
+}
+
+extern "C" int dgtta_gin_layer_fwd(const float *x_dev, float *out_dev, const float *ker_host, const float *shift_host,
+                                   int B, int cin, int cout, int k, int D, int H, int W, int use_act,
+                                   void *workspace_dev, size_t workspace_bytes, dgtta_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x_dev || !out_dev || !ker_host || !shift_host || !workspace_dev) { set_error("dgtta_gin_layer_fwd: null pointer"); return DGTTA_ENULL; }
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (k != 1 && k != 3)) { set_error("dgtta_gin_layer_fwd: bad shape"); return DGTTA_EINVAL; }
+    if (cin > GIN_MAXC || cout > GIN_MAXC) { set_error("dgtta_gin_layer_fwd: more than %d channels not supported", GIN_MAXC); return DGTTA_EUNSUPPORTED; }
+    if ((size_t)B * D > 65535u || (size_t)D * H * W >= (size_t)1 << 31) { set_error("dgtta_gin_layer_fwd: volume too large"); return DGTTA_EINVAL; }
+    const size_t nker = (size_t)cout * B * cin * k * k * k, nshift = (size_t)cout * B;
+    if (workspace_bytes < (nker + nshift) * sizeof(float)) { set_error("dgtta_gin_layer_fwd: workspace too small"); return DGTTA_EWORKSPACE; }
+    float *wts = (float *)workspace_dev;
+    cudaError_t e = cudaMemcpyAsync(wts, ker_host, nker * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(wts + nker, shift_host, nshift * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { set_error("dgtta_gin_layer_fwd: params upload: %s", cudaGetErrorString(e)); return (int)e; }
+    GinLayerParams P;
+    P.in = x_dev; P.out = out_dev; P.wts = wts; P.x0 = nullptr; P.alphas = nullptr; P.partials = nullptr;
+    P.B = B; P.cin = cin; P.cout = cout; P.D = D; P.H = H; P.W = W; P.act = use_act ? 1 : 0; P.last = 0;
+    const dim3 block(GIN_BX, GIN_BY, 1);
+    const dim3 grid((W + GIN_BX - 1) / GIN_BX, (H + GIN_BY - 1) / GIN_BY, B * D);
+    if (k == 1) gin_layer_kernel<1><<<grid, block, 0, stream>>>(P);
+    else gin_layer_kernel<3><<<grid, block, 0, stream>>>(P);
+    return check_launch("gin_layer_kernel");
+}

@@ -1,0 +1,90 @@
+"""View augmentation of the TTA consistency loop — drop-in for the live part of
+dg_tta/tta/augmentation_utils.py (get_rand_affine :156-170, gin_mind_aug :173-174) plus the
+affine_grid + grid_sample op pair the reference writes inline (tta.py:523-551,571-575;
+torch_utils.py:55-73), fused here into `affine_grid_sample`.
+
+The deformable branch of the reference (augmentation_utils.py:8-153) is dead code there
+(get_disp_field raises TypeError) and is not rebuilt.
+"""
+import torch
+
+from .. import _lib
+from ..gin import GINGroupConv, _GIN_CFG
+from ..mind import mind_ssc
+
+_INTERP = {"bilinear": 0, "nearest": 1}
+_PAD = {"zeros": 0, "border": 1}
+
+
+def get_rand_affine(batch_size, strength=0.05, flip=False):
+    """augmentation_utils.py:156-170 — host draws in the same order; returns (R[:, :3], R^-1[:, :3])."""
+    affine = torch.cat(
+        (torch.randn(batch_size, 3, 4) * strength + torch.eye(3, 4).unsqueeze(0),
+         torch.tensor([0, 0, 0, 1]).view(1, 1, 4).repeat(batch_size, 1, 1)), 1)
+    if flip:
+        signs = 2 * (torch.rand(3) > 0.5).float() - 1
+        affine = affine @ torch.diag(torch.cat([signs, torch.tensor([1.0])]))
+    return affine[:, :3], affine.inverse()[:, :3]
+
+
+def _theta_on(device, theta, B):
+    if tuple(theta.shape) != (B, 3, 4):
+        raise ValueError(f"theta must have shape [{B},3,4], got {tuple(theta.shape)}")
+    return theta.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class _AffineSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, theta, out_size, interp, padding):
+        L = _lib.lib()
+        B, C, Di, Hi, Wi = input.shape
+        Do, Ho, Wo = out_size
+        x = input.contiguous()
+        with torch.cuda.device(x.device):
+            out = torch.empty((B, C, Do, Ho, Wo), device=x.device, dtype=torch.float32)
+            rc = L.dgtta_affine_sample_fwd(x.data_ptr(), theta.data_ptr(), out.data_ptr(), B, C, Di, Hi, Wi,
+                                           Do, Ho, Wo, interp, padding, _lib.stream_ptr())
+            _lib.check(rc, "dgtta_affine_sample_fwd")
+        ctx.save_for_backward(theta)
+        ctx.geom = (B, C, Di, Hi, Wi, Do, Ho, Wo, interp, padding)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (theta,) = ctx.saved_tensors
+        B, C, Di, Hi, Wi, Do, Ho, Wo, interp, padding = ctx.geom
+        if interp != 0:
+            return torch.zeros((B, C, Di, Hi, Wi), device=grad_out.device), None, None, None, None
+        L = _lib.lib()
+        g = grad_out.contiguous().to(torch.float32)
+        with torch.cuda.device(g.device):
+            grad_in = torch.empty((B, C, Di, Hi, Wi), device=g.device, dtype=torch.float32)
+            rc = L.dgtta_affine_sample_bwd_input(g.data_ptr(), theta.data_ptr(), grad_in.data_ptr(), B, C, Di, Hi,
+                                                 Wi, Do, Ho, Wo, padding, _lib.stream_ptr())
+            _lib.check(rc, "dgtta_affine_sample_bwd_input")
+        return grad_in, None, None, None, None
+
+
+def affine_grid_sample(input, theta, out_size=None, mode="bilinear", padding_mode="zeros", align_corners=False):
+    """F.grid_sample(input, F.affine_grid(theta, out_size, align_corners=False), mode, padding_mode,
+    align_corners=False) in one kernel, differentiable w.r.t. `input` (not theta — the reference never
+    needs that gradient).  theta [B,3,4] may live on the host (as get_rand_affine returns it)."""
+    if align_corners:
+        raise NotImplementedError("the reference only uses align_corners=False")
+    _lib.require_cuda_f32(input, "input")
+    if input.dim() != 5:
+        raise ValueError("affine_grid_sample expects [B,C,D,H,W]")
+    if mode not in _INTERP or padding_mode not in _PAD:
+        raise ValueError(f"unsupported mode/padding_mode: {mode}/{padding_mode}")
+    B = input.shape[0]
+    size = tuple(int(v) for v in (out_size[-3:] if out_size is not None else input.shape[-3:]))
+    theta = _theta_on(input.device, theta, B)
+    return _AffineSample.apply(input, theta, size, _INTERP[mode], _PAD[padding_mode])
+
+
+def gin_mind_aug(input):
+    """augmentation_utils.py:173-174: MIND3D()(gin_aug(input)).  GIN's final rescale is deferred
+    into MIND's loads (one pass over the volume less); the values MIND sees are bit-identical to the
+    unfused chain because the same two multiplications are applied in the same order."""
+    mixed, scale = GINGroupConv(dict(_GIN_CFG))(input, defer_scale=True)
+    return mind_ssc(mixed, in_scale=scale)

@@ -1,0 +1,119 @@
+/*
+ * dgtta.h — C ABI of libdgtta_sm100.so: the B200 (sm_100a) implementation of DG-TTA's
+ * input-transform hot path (MIND-SSC descriptor, GIN augmentation, affine trilinear sampling).
+ *
+ * Conventions:
+ *   - plain C symbols, raw pointers and sizes, no torch / C++ types;
+ *   - every tensor is contiguous NCDHW float32; "dev" pointers are CUDA device pointers of the
+ *     current device, "host" pointers are ordinary host memory read before the call returns;
+ *   - the library never allocates device memory: outputs and workspaces are caller-owned
+ *     (query *_workspace_bytes first); it only enqueues kernels on `stream` and never syncs;
+ *   - return value 0 = ok, >0 = cudaError_t from a launch, <0 = DGTTA_E* argument error;
+ *     dgtta_last_error() gives the message of the last failure on the calling thread.
+ *
+ * Each entry point names the reference interface (multimodallearning/DG-TTA, file:line) it replaces.
+ */
+#ifndef DGTTA_H_
+#define DGTTA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *dgtta_stream_t; /* == cudaStream_t */
+
+#define DGTTA_ABI_VERSION 1
+
+#define DGTTA_EINVAL (-1)     /* bad shape / parameter */
+#define DGTTA_ENULL (-2)      /* required pointer is NULL */
+#define DGTTA_EWORKSPACE (-3) /* workspace too small */
+#define DGTTA_EUNSUPPORTED (-4)
+
+/* MIND noise source (dg_tta/mind.py:150-152) */
+#define DGTTA_NOISE_NONE 0   /* randn_weighting ignored: E = I(p+s1) - I(p+s2)            */
+#define DGTTA_NOISE_TENSOR 1 /* noise_dev holds the [B,12,D,H,W] normal field              */
+#define DGTTA_NOISE_PHILOX 2 /* regenerate torch's CUDA randn stream in-kernel (seed, offset) */
+
+/* sampler modes (torch.nn.functional.grid_sample arguments used at tta.py:549,573; torch_utils.py:59,71) */
+#define DGTTA_INTERP_TRILINEAR 0
+#define DGTTA_INTERP_NEAREST 1
+#define DGTTA_PAD_ZEROS 0
+#define DGTTA_PAD_BORDER 1
+
+int dgtta_abi_version(void);
+const char *dgtta_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * MIND-SSC descriptor.  Replaces MIND3D.forward (dg_tta/mind.py:142-164) including the shift
+ * kernels built in MIND3D.__init__ (:98-140), smooth/filter1D (:5-43) and therefore mind_hook
+ * (:167-168).
+ *   img_dev   [B,1,D,H,W]        out_dev [B,12,D,H,W]
+ *   in_scale_dev: NULL, or [B,2] floats (a_b, c_b): the kernel reads I = (img * a_b) * c_b — the
+ *                 deferred Frobenius re-normalisation of GIN (gin.py:228) when GIN feeds MIND.
+ *   taps_host [ntaps] Gaussian taps (mind.py:27-37), ntaps odd, 1..9
+ *   noise_mode/noise_dev/philox_*: see DGTTA_NOISE_*.  For PHILOX, (seed, offset) are the device
+ *                 generator's state before the draw; the caller advances the generator by
+ *                 dgtta_mind_philox_offset_increment() afterwards.
+ *   workspace: dgtta_mind_workspace_bytes(B,D,H,W) bytes, 16-byte aligned.
+ * Two launches: a speculative fused stencil pass that also reduces the statistics of the
+ * per-voxel variance, then a fix-up pass that recomputes only the tiles in which the global
+ * clamp of mind.py:158-160 is active (none for ordinary images).
+ * ------------------------------------------------------------------------------------------- */
+size_t dgtta_mind_workspace_bytes(int B, int D, int H, int W);
+int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const float *in_scale_dev, int B, int D, int H,
+                       int W, int delta, const float *taps_host, int ntaps, float randn_weighting,
+                       int noise_mode, const float *noise_dev, uint64_t philox_seed, uint64_t philox_offset,
+                       void *workspace_dev, size_t workspace_bytes, dgtta_stream_t stream);
+/* how far torch.randn_like(edge_selection) advances the CUDA generator offset for this shape
+ * (ATen/native/cuda/DistributionTemplates.h calc_execution_policy); sm_count/max_threads_per_sm
+ * are the device properties torch uses. */
+uint64_t dgtta_mind_philox_offset_increment(int B, int D, int H, int W, int sm_count, int max_threads_per_sm);
+
+/* ---------------------------------------------------------------------------------------------
+ * GIN augmentation.  Replaces GINGroupConv.forward (dg_tta/gin.py:168-230) and the per-layer
+ * GradlessGCReplayNonlinBlock.forward (gin.py:59-122) for 5-D input; the random draws stay with
+ * the caller (reference order: alphas on the device generator, then per layer randint/randn/randn
+ * on the CPU generator).
+ *   x_dev [B,Cin,D,H,W]   out_dev same shape
+ *   params_host: for layer L = 0..n_layer-1: ker_L [cout_L*B, cin_L, k,k,k] then shift_L [cout_L*B]
+ *   ksizes_host [n_layer] each 1 or 3;   alphas_dev [B]
+ *   scale_out_dev: NULL -> out = mixed * (1/(||mixed_b||+1e-5)) * ||x_b|| (gin.py:228);
+ *                  non-NULL -> out = mixed (unscaled) and scale_out_dev[b] = {1/(||mixed_b||+1e-5), ||x_b||}
+ *                  for a consumer that applies it on load (dgtta_mind_ssc_fwd in_scale_dev).
+ * ------------------------------------------------------------------------------------------- */
+size_t dgtta_gin_workspace_bytes(int B, int D, int H, int W, int in_channels, int n_layer, int interm_channels);
+int dgtta_gin_fwd(const float *x_dev, float *out_dev, const float *params_host, const int *ksizes_host,
+                  const float *alphas_dev, int B, int D, int H, int W, int in_channels, int n_layer,
+                  int interm_channels, float *scale_out_dev, void *workspace_dev, size_t workspace_bytes,
+                  dgtta_stream_t stream);
+
+/* One GIN layer on its own.  Replaces GradlessGCReplayNonlinBlock.forward (dg_tta/gin.py:59-122, 3-D
+ * branch): grouped conv (groups=B, zero padding k//2) + shift + optional leaky_relu(0.01).
+ *   x_dev [B,cin,D,H,W] -> out_dev [B,cout,D,H,W]; ker_host [cout*B,cin,k,k,k]; shift_host [cout*B]
+ *   workspace: (cout*B*cin*k^3 + cout*B) * 4 bytes. */
+int dgtta_gin_layer_fwd(const float *x_dev, float *out_dev, const float *ker_host, const float *shift_host, int B,
+                        int cin, int cout, int k, int D, int H, int W, int use_act, void *workspace_dev,
+                        size_t workspace_bytes, dgtta_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Affine view warp.  Replaces the F.affine_grid + F.grid_sample pairs at dg_tta/tta/tta.py:
+ * 523-532 + 548-551 (image, border), :571-575 (prediction, zeros, differentiable w.r.t. input)
+ * and dg_tta/tta/torch_utils.py:55-73 (patch crop; nearest for labels), align_corners=False.
+ * No grid tensor exists: coordinates come from theta in-kernel.
+ *   in_dev [B,C,Di,Hi,Wi]  theta_dev [B,3,4]  out_dev [B,C,Do,Ho,Wo]
+ * bwd_input: grad_in_dev [B,C,Di,Hi,Wi] is overwritten with the adjoint of the trilinear forward.
+ * ------------------------------------------------------------------------------------------- */
+int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_dev, float *out_dev, int B, int C, int Di,
+                            int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding,
+                            dgtta_stream_t stream);
+int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const float *theta_dev, float *grad_in_dev, int B,
+                                  int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int padding,
+                                  dgtta_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGTTA_H_ */

@@ -1,0 +1,97 @@
+"""Affine sampler parity (forward modes, adjoint) vs golden fixtures (torch affine_grid+grid_sample run by
+the reference's op sequence) and the oracle.  Tolerance 5e-5*max|x|: the reference itself adds and
+subtracts the identity grid (tta.py:523-532,548), perturbing coordinates by ~1e-7*size voxels."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import cuda, synth_volume
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tta_view_warp_forward_and_backward():
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample
+    g = load_golden("affine_view")
+    img = affine_grid_sample(cuda(g["imgs"]), torch.from_numpy(g["R"]), padding_mode="border")
+    assert np.abs(img.cpu().numpy() - g["imgs_aug"]).max() <= 2e-5
+    lg = cuda(g["logits"]).requires_grad_(True)
+    warped = affine_grid_sample(lg, torch.from_numpy(g["R_inv"]))
+    assert np.abs(warped.detach().cpu().numpy() - g["warped"]).max() <= 5e-5
+    (warped * cuda(g["grad_out"])).sum().backward()
+    assert np.abs(lg.grad.cpu().numpy() - g["grad_logits"]).max() <= 5e-5
+
+
+def test_general_modes_and_sizes():
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample
+    g = load_golden("affine_general")
+    src, theta, size = cuda(g["src"]), torch.from_numpy(g["theta"]), g["out_size"].tolist()
+    for mode in ("bilinear", "nearest"):
+        for pad in ("zeros", "border"):
+            out = affine_grid_sample(src, theta, size, mode=mode, padding_mode=pad).cpu().numpy()
+            ref = g[f"{mode}_{pad}"]
+            if mode == "nearest":
+                assert (out != ref).mean() <= 0.002
+            else:
+                assert np.abs(out - ref).max() <= 2e-5
+    for pad in ("zeros", "border"):
+        s = src.clone().requires_grad_(True)
+        out = affine_grid_sample(s, theta, size, padding_mode=pad)
+        (out * cuda(g["grad_out"])).sum().backward()
+        assert np.abs(s.grad.cpu().numpy() - g[f"grad_src_{pad}"]).max() <= 5e-5
+
+
+def test_identity_is_exact_and_adjoint_property():
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample
+    x = synth_volume((2, 3, 17, 18, 19), 4).cuda()
+    eye = torch.eye(3, 4)[None].repeat(2, 1, 1)
+    y = affine_grid_sample(x, eye, padding_mode="border")
+    assert (y - x).abs().max() <= 2e-6
+    # <A x, g> == <x, A^T g>
+    torch.manual_seed(0)
+    theta = eye + 0.1 * torch.randn(2, 3, 4)
+    g = torch.randn_like(x)
+    xr = x.clone().requires_grad_(True)
+    out = affine_grid_sample(xr, theta)
+    (out * g).sum().backward()
+    lhs = float((out.detach().double() * g.double()).sum())
+    rhs = float((x.double() * xr.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_against_oracle_full_patch():
+    """config-3 shapes (2x1x128^3 image, 2x14x128^3 logits is too big for the CPU oracle in seconds ->
+    2x4 channels) through the C oracle"""
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine
+    from oracle import cform
+    torch.manual_seed(7)
+    R, Ri = get_rand_affine(2)
+    x = synth_volume((2, 1, 128, 128, 128), 31)
+    out = affine_grid_sample(x.cuda(), R, padding_mode="border").cpu().numpy()
+    ref = cform.affine_sample(x.numpy(), R.numpy(), x.shape, padding_mode="border")
+    assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
+    lg = synth_volume((2, 4, 64, 72, 80), 32)
+    out = affine_grid_sample(lg.cuda(), Ri).cpu().numpy()
+    ref = cform.affine_sample(lg.numpy(), Ri.numpy(), lg.shape)
+    assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
+    go = synth_volume((2, 4, 64, 72, 80), 33)
+    s = lg.cuda().requires_grad_(True)
+    (affine_grid_sample(s, Ri) * go.cuda()).sum().backward()
+    gref = cform.affine_sample_bwd_input(go.numpy(), Ri.numpy(), lg.shape)
+    assert np.abs(s.grad.cpu().numpy() - gref).max() <= 5e-5 * max(1.0, np.abs(gref).max())
+
+
+def test_gin_mind_aug_fused_chain():
+    from dg_tta_b200.gin import gin_forward
+    from dg_tta_b200 import mind_ssc
+    from conftest import gin_layers
+    g = load_golden("gin_mind_aug")
+    kers, shifts = gin_layers(g)
+    mixed, scale = gin_forward(cuda(g["x"]), [torch.from_numpy(k) for k in kers], [torch.from_numpy(s) for s in shifts],
+                               cuda(g["alphas"]), 2, defer_scale=True)
+    out = mind_ssc(mixed, noise=cuda(g["noise"]), in_scale=scale).cpu().numpy()
+    assert np.abs(out - g["out"]).max() <= 5e-5   # chained fp32 stages; see tests/test_oracle_golden.py
+    from dg_tta_b200.tta.augmentation_utils import gin_mind_aug
+    res = gin_mind_aug(cuda(g["x"]))
+    assert tuple(res.shape) == tuple(g["out"].shape) and not torch.isnan(res).any()

@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Developer probe: CUDA-event timings of the individual kernels (not the bench contract; see bench.py)."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tests"))
+from dg_tta_b200 import mind_ssc  # noqa: E402
+from dg_tta_b200.gin import GINGroupConv, gin_forward  # noqa: E402
+from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine  # noqa: E402
+from gpu_util import synth_volume  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    res = {}
+    for shape in [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]:
+        x = synth_volume(shape, 1).cuda()
+        vox = x.numel()
+        for delta in (1, 2):
+            med, best = timeit(lambda: mind_ssc(x, delta=delta, noise=False))
+            res[f"mind_clean_d{delta}_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6, gbs=vox * 52 / med / 1e6)
+        noise = torch.randn((shape[0], 12) + shape[2:], device="cuda")
+        med, best = timeit(lambda: mind_ssc(x, noise=noise))
+        res[f"mind_noise_tensor_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6, gbs=vox * 100 / med / 1e6)
+        med, best = timeit(lambda: mind_ssc(x))
+        res[f"mind_default_randn_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6)
+    x = synth_volume((2, 1, 192, 192, 192), 2).cuda()
+    net = GINGroupConv(dict(IN_CHANNELS=1, N_LAYER=4, INTERM_CHANNELS=2))
+    for want in ([1, 1, 1, 1], [3, 3, 3, 3], [3, 1, 3, 1]):
+        seed = 0
+        while True:
+            torch.manual_seed(seed)
+            alphas, kers, shifts = net.draw(x)
+            if [k.shape[-1] for k in kers] == want:
+                break
+            seed += 1
+        med, best = timeit(lambda: gin_forward(x, kers, shifts, alphas, 2))
+        res["gin_k" + "".join(map(str, want))] = dict(ms=med, best=best, gvox_s=x.numel() / med / 1e6, gbs=x.numel() * 8 / med / 1e6)
+    torch.manual_seed(0)
+    R, Ri = get_rand_affine(2)
+    img = synth_volume((2, 1, 128, 128, 128), 3).cuda()
+    med, best = timeit(lambda: affine_grid_sample(img, R, padding_mode="border"))
+    res["sample_img_border_2x128"] = dict(ms=med, best=best, gbs=img.numel() * 8 / med / 1e6)
+    lg = torch.randn(2, 14, 128, 128, 128, device="cuda", requires_grad=True)
+    med, best = timeit(lambda: affine_grid_sample(lg, Ri))
+    res["sample_logits_fwd_2x14x128"] = dict(ms=med, best=best, gbs=lg.numel() * 8 / med / 1e6)
+    out = affine_grid_sample(lg, Ri)
+    go = torch.randn_like(out)
+    med, best = timeit(lambda: torch.autograd.grad(out, lg, go, retain_graph=True))
+    res["sample_logits_bwd_2x14x128"] = dict(ms=med, best=best, gbs=lg.numel() * 12 / med / 1e6)
+    # torch eager comparison for the sampler
+    import torch.nn.functional as F
+    Rd = R.cuda()
+    med, best = timeit(lambda: F.grid_sample(img, F.affine_grid(Rd, list(img.shape), align_corners=False), padding_mode="border", align_corners=False))
+    res["torch_sample_img_border_2x128"] = dict(ms=med, best=best)
+    for k, v in res.items():
+        print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
+
+
+if __name__ == "__main__":
+    main()
