@@ -1,0 +1,602 @@
+// MIND-SSC descriptor — tuned sm_100a kernel for the reference's configuration: 5-tap Gaussian
+// (sigma = 1, dg_tta/mind.py:31) and dilation delta in {1,2,3}.  Math: see mind_ssc.cu.
+//
+// One CTA (512 threads, one per SM) owns a 16 x 32 patch of the H-W plane and marches along D in
+// batches of PB = 4 planes.  All arithmetic is packed fp32x2 (FFMA2/FMUL2/FADD2).  Per batch:
+//   T  cp.async ring of raw image planes: tile[slot][20+2d][44] holds I at clamped coordinates
+//      (replicate padding of mind.py:137 is folded into the addresses); only PB new planes per batch.
+//   S1 720 tasks (plane, halo row, 4 columns): the task loads the 6-neighbourhood of its 4 positions
+//      (LDS.128) and writes the 12 squared edge channels -> ws[plane][c][row][col] (STS.128).
+//   S2 432 tasks (plane, channel, 4-column strip): H smoothing with a sliding 5-row register window, in
+//      place (LDS.128 / STS.128), exactly one task per thread.
+//   C  warp = patch row; thread = (4 consecutive voxels) x (3 channels); lanes = 8 column groups x 4
+//      channel groups.  Per plane: 2 LDS.128 per channel give 4 W-smoothed values; the D smoothing runs
+//      on a 4-slot register window (slots are compile-time because PB == taps - 1); min / mean over the 12
+//      channels by two xor-shuffles; exp; one STG.128 per channel (full 128-byte lines per warp).
+// Three __syncthreads per 4 planes; the only HBM traffic is 4 B/voxel in (+halo via L2) and 48 B/voxel out.
+//
+// Global clamp (mind.py:158-160): pass 1 assumes it inactive and records {sum v, min positive v, max v}
+// per (CTA, batch).  mind_fast_finalize reduces them to mean_all(v) and lists the (CTA, batch) units whose
+// range leaves [0.001*mean, 1000*mean]; pass 2 recomputes exactly those 4-plane units with the clamp.
+#include "mind_internal.cuh"
+
+namespace dgtta {
+
+namespace fast {
+
+constexpr int R = 2, NT = 5, PB = 4, NWIN = NT - 1;   // PB == NWIN keeps the D-window slots compile-time
+constexpr int EH = MIND_TH + 2 * R;   // 20 halo rows
+constexpr int EW = MIND_TW + 2 * R;   // 36 halo columns
+constexpr int TWD = 44;               // tile row pitch: 4 pad + 36 + 4 pad words (conflict-free LDS.128 across rows)
+constexpr int WSP = EW;                    // ws row pitch 36: rows 4 banks apart -> conflict-free LDS/STS.128 across rows
+constexpr int WS_CH = EH * WSP + 8;        // 728: channel pitch == 24 (mod 32) -> the 4 channel groups of a warp hit disjoint banks
+constexpr int WS_PLANE = 12 * WS_CH;
+constexpr int NQUAD = EW / 4;              // 9 position quads per halo row
+constexpr int S1_TASKS = PB * EH * NQUAD;  // 720
+constexpr int S2_TASKS = PB * 12 * NQUAD;  // 432 column-strip tasks: a single round
+constexpr int C_WARPS = MIND_TH;           // 16 warps own the patch rows in stage C
+constexpr int NTHREADS = MIND_THREADS;     // 512
+static_assert(S2_TASKS <= NTHREADS, "S2 must fit one round");
+
+template <int DELTA>
+struct Geom {
+    static constexpr int TR = EH + 2 * DELTA;        // tile rows
+    static constexpr int TCOLS = EW + 2 * DELTA;     // loaded tile columns
+    static constexpr int NSLOT = PB + 2 * DELTA;     // ring of image planes
+    static constexpr int TILE = TR * TWD;
+    static constexpr int CELLS = TR * TCOLS;
+    static constexpr int NCELL = (CELLS + NTHREADS - 1) / NTHREADS;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(PB * WS_PLANE + NSLOT * TILE);
+};
+
+struct Params {
+    const float *img;
+    float *out;
+    const float *noise;
+    const float *in_scale;
+    float4 *stats;        // [ncta * nbatch] {sum v, min positive v, max v, -}
+    const int *fix_hdr;   // {count} then list of unit ids (FIX pass)
+    const float *fix_lohi;
+    int B, D, H, W;
+    int nTH, nTW, nCD, chunkD, nbatch;
+    float rw;
+    float taps[NT];
+};
+
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void ld4(const float *p, float *v)
+{
+    const float4 f = *reinterpret_cast<const float4 *>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): two lanes per issue slot.  The FP32 pipe still
+// retires 128 lane-ops/clk/SM (measured, tools/microbench/ffma2.cu), but the freed issue slots carry the
+// LDS/STS/SHFL/MUFU traffic of the stencil.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+__device__ __forceinline__ void ld4p(const float *p, u64 &a, u64 &b)
+{
+    const float4 f = *reinterpret_cast<const float4 *>(p);
+    a = pk(f.x, f.y); b = pk(f.z, f.w);
+}
+__device__ __forceinline__ void st4p(float *p, u64 a, u64 b)
+{
+    float4 f;
+    unpk(a, f.x, f.y); unpk(b, f.z, f.w);
+    *reinterpret_cast<float4 *>(p) = f;
+}
+
+// March one CTA over output planes [d0, d1) of patch (h0, w0) of sample b.
+template <int DELTA, int NOISE, bool FIX>
+__device__ __forceinline__ void process(const Params &P, float *smem, float (*red)[C_WARPS], int b, int h0,
+                                        int w0, int d0, int d1, float lo, float hi, float4 *stats)
+{
+    using G = Geom<DELTA>;
+    float *ws = smem;
+    float *tiles = smem + PB * WS_PLANE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = P.D, H = P.H, W = P.W, HW = H * W;
+    const float *img = P.img + (size_t)b * D * HW;
+
+    u64 G2[NT];   // taps broadcast to both halves (uniform -> FFMA2 takes them as UR.F32 operands)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) G2[t] = pk(P.taps[t], P.taps[t]);
+
+    // ---- T: per-thread tile cells (plane-invariant)
+    int cell_s[G::NCELL], cell_g[G::NCELL];
+#pragma unroll
+    for (int k = 0; k < G::NCELL; ++k) {
+        const int i = tid + k * NTHREADS;
+        if (i < G::CELLS) {
+            const int rr = i / G::TCOLS, cc = i - rr * G::TCOLS;
+            cell_s[k] = rr * TWD + (4 - DELTA) + cc;
+            cell_g[k] = clampi(h0 - R - DELTA + rr, 0, H - 1) * W + clampi(w0 - R - DELTA + cc, 0, W - 1);
+        } else {
+            cell_s[k] = -1;
+            cell_g[k] = 0;
+        }
+    }
+    int loaded_hi;  // highest real plane resident in the ring
+    auto load_until = [&](int need_hi) {
+        need_hi = min(need_hi, D - 1);
+        for (int p = loaded_hi + 1; p <= need_hi; ++p) {
+            float *dst = tiles + (p % G::NSLOT) * G::TILE;
+            const float *src = img + (size_t)p * HW;
+#pragma unroll
+            for (int k = 0; k < G::NCELL; ++k)
+                if (cell_s[k] >= 0) cp_async4(dst + cell_s[k], src + cell_g[k]);
+        }
+        loaded_hi = max(loaded_hi, need_hi);
+        cp_async_commit();
+    };
+
+    // halo rows / columns outside the volume replicate E^2 of the clamped position (mind.py:22)
+    const int rT = max(0, R - h0), rB = min(EH - 1, H - 1 - h0 + R);
+    const int eR = W - 1 - w0 + R;               // halo column index of w = W-1
+    const bool scaled = P.in_scale != nullptr;
+    u64 SA = pk(1.f, 1.f), SC = SA;
+    if (scaled) { SA = pk(P.in_scale[2 * b], P.in_scale[2 * b]); SC = pk(P.in_scale[2 * b + 1], P.in_scale[2 * b + 1]); }
+    const u64 RW = pk(P.rw, P.rw);
+
+    // ---- S2 bookkeeping: one (plane, channel, column quad) task per thread, exactly one round
+    const bool s2_active = tid < S2_TASKS;
+    const int s2_pc = tid / NQUAD;                   // pz * 12 + c
+    const int s2_pz = s2_pc / 12;
+    const int s2_off = s2_pz * WS_PLANE + (s2_pc - s2_pz * 12) * WS_CH + 4 * (tid - s2_pc * NQUAD);
+
+    // ---- C bookkeeping: warp = patch row, lane = (4-column group wl, channel group cg)
+    const bool c_active = warp < C_WARPS;
+    const int wl = lane & 7, cg = lane >> 3;
+    const int c_off = (3 * cg) * WS_CH + warp * WSP + 4 * wl;
+    const int vh = h0 + warp, vw = w0 + 4 * wl;
+    const bool row_ok = c_active && vh < H;
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = row_ok && (vw + k < W);
+    // per-channel output pointers of the thread's 4-voxel run, advanced plane by plane
+    float *op0 = P.out + (((size_t)b * 12 + 3 * cg) * D + d0) * HW + (size_t)vh * W + vw;
+    const size_t ch_stride = (size_t)D * HW;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && ((W & 3) == 0);
+
+    u64 win[3][2][NWIN];   // the last 4 W-smoothed planes of the thread's 4 voxels x 3 channels
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < NWIN; ++t) win[a][j][t] = 0ull;
+
+    const int z_begin = d0 - R, z_end = d1 + R;
+    const int nb = (z_end - z_begin + PB - 1) / PB;
+
+    // first batch: everything it needs
+    loaded_hi = max(clampi(z_begin, 0, D - 1) - DELTA, 0) - 1;
+    load_until(clampi(z_begin + PB - 1, 0, D - 1) + DELTA);
+
+    for (int n = 0; n < nb; ++n) {
+        const int zb = z_begin + n * PB;
+        cp_async_wait_all();
+        __syncthreads();   // tiles of this batch visible; every thread finished C of the previous batch
+        if (!FIX && n > 0 && warp == 0) {
+            // statistics of the previous batch (warp partials were parked in `red` before the barrier)
+            float s = lane < C_WARPS ? red[0][lane] : 0.f;
+            float mnv = lane < C_WARPS ? red[1][lane] : __int_as_float(0x7f800000);
+            float mxv = lane < C_WARPS ? red[2][lane] : 0.f;
+            s = warp_sum(s); mnv = warp_min(mnv); mxv = warp_max(mxv);
+            if (lane == 0) stats[n - 1] = make_float4(s, mnv, mxv, 0.f);
+        }
+
+        // ================= S1: squared edges of 4 positions x 12 channels per task
+#pragma unroll 1
+        for (int t = tid; t < S1_TASKS; t += NTHREADS) {
+            const int pz = t / (EH * NQUAD);
+            const int rem = t - pz * (EH * NQUAD);
+            const int r = rem / NQUAD, q = rem - r * NQUAD;
+            if (zb + pz >= z_end) continue;
+            const int zc = clampi(zb + pz, 0, D - 1);
+            const int rc = clampi(r, rT, rB);
+            const int toff = (rc + DELTA) * TWD + 4 + 4 * q;   // centre row, first position of the quad
+            const float *tc = tiles + (zc % G::NSLOT) * G::TILE + toff;
+            const float *tm = tiles + (clampi(zc - DELTA, 0, D - 1) % G::NSLOT) * G::TILE + toff;
+            const float *tp = tiles + (clampi(zc + DELTA, 0, D - 1) % G::NSLOT) * G::TILE + toff;
+            u64 nbv[6][2];   // D-, D+, H-, H+, W-, W+ as (k0,k1),(k2,k3)
+            ld4p(tm, nbv[NB_DM][0], nbv[NB_DM][1]);
+            ld4p(tp, nbv[NB_DP][0], nbv[NB_DP][1]);
+            ld4p(tc - DELTA * TWD, nbv[NB_HM][0], nbv[NB_HM][1]);
+            ld4p(tc + DELTA * TWD, nbv[NB_HP][0], nbv[NB_HP][1]);
+            float wr[12];      // centre row, positions -4 .. 7 relative to the quad
+            ld4(tc - 4, &wr[0]); ld4(tc, &wr[4]); ld4(tc + 4, &wr[8]);
+            float wm[4], wp[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { wm[k] = wr[4 + k - DELTA]; wp[k] = wr[4 + k + DELTA]; }
+            if (w0 == 0 && q == 0) {
+                // columns w = -2,-1 take E of w = 0: only the W+ neighbour differs from the clamped loads
+                wp[0] = wp[2]; wp[1] = wp[2];
+            }
+            if (4 * q + 3 > eR) {
+                // columns beyond w = W-1 take E of w = W-1: only the W- neighbour differs
+                const float wm_fix = tiles[(zc % G::NSLOT) * G::TILE + (rc + DELTA) * TWD + 4 + eR - DELTA];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (4 * q + k > eR) wm[k] = wm_fix;
+            }
+            nbv[NB_WM][0] = pk(wm[0], wm[1]); nbv[NB_WM][1] = pk(wm[2], wm[3]);
+            nbv[NB_WP][0] = pk(wp[0], wp[1]); nbv[NB_WP][1] = pk(wp[2], wp[3]);
+            if (scaled) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) nbv[a][j] = fmul2(fmul2(nbv[a][j], SA), SC);
+            }
+            float *wsp = ws + pz * WS_PLANE + r * WSP + 4 * q;
+            const float *nz = nullptr;
+            int ngw[4];
+            if (NOISE == DGTTA_NOISE_TENSOR) {
+                nz = P.noise + ((size_t)b * 12 * D + zc) * HW + (size_t)clampi(h0 - R + r, 0, H - 1) * W;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ngw[k] = clampi(w0 - R + 4 * q + k, 0, W - 1);
+            }
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
+                u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
+                if (NOISE == DGTTA_NOISE_TENSOR) {
+                    const float *np = nz + (size_t)c * D * HW;
+                    // mind.py:150-152: edge + rw * noise, product and sum rounded separately
+                    e0 = fadd2(e0, fmul2(RW, pk(__ldg(np + ngw[0]), __ldg(np + ngw[1]))));
+                    e1 = fadd2(e1, fmul2(RW, pk(__ldg(np + ngw[2]), __ldg(np + ngw[3]))));
+                }
+                st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
+            }
+        }
+        __syncthreads();
+
+        // ================= S2: H smoothing of a 4-column strip, in place, sliding 5-row register window
+        if (s2_active && zb + s2_pz < z_end) {
+            float *col = ws + s2_off;
+            u64 x[NT][2];
+#pragma unroll
+            for (int r = 0; r < EH; ++r) {
+                ld4p(col + r * WSP, x[r % NT][0], x[r % NT][1]);
+                if (r >= NT - 1) {
+                    const int o = r - (NT - 1);
+                    u64 a0 = fmul2(x[o % NT][0], G2[0]), a1 = fmul2(x[o % NT][1], G2[0]);
+#pragma unroll
+                    for (int t = 1; t < NT; ++t) {
+                        a0 = ffma2(x[(o + t) % NT][0], G2[t], a0);
+                        a1 = ffma2(x[(o + t) % NT][1], G2[t], a1);
+                    }
+                    st4p(col + o * WSP, a0, a1);   // row o is dead as an input from here on
+                }
+            }
+        }
+        __syncthreads();   // ws complete; tiles no longer read in this batch
+
+        // prefetch the image planes of the next batch while C runs
+        if (n + 1 < nb) load_until(clampi(zb + 2 * PB - 1, 0, D - 1) + DELTA);
+
+        // ================= C: W smoothing, D window, MIND normalisation, store
+        float st_sum = 0.f, st_min = __int_as_float(0x7f800000), st_max = 0.f;
+        if (c_active) {
+#pragma unroll
+            for (int ph = 0; ph < PB; ++ph) {
+                const int z = zb + ph;
+                if (z < z_end) {
+                    const float *wsp = ws + ph * WS_PLANE + c_off;
+                    const int d = z - R;
+                    const bool emit = d >= d0;   // uniform
+                    u64 m[3][2];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        float v[8];
+                        ld4(wsp + a * WS_CH, &v[0]);
+                        ld4(wsp + a * WS_CH + 4, &v[4]);
+                        // o_k = g2 v[k+2] + g1 (v[k+1] + v[k+3]) + g0 (v[k] + v[k+4]),  k = 0..3, two lanes at a time
+                        const u64 s0a = fadd2(pk(v[0], v[1]), pk(v[4], v[5]));
+                        const u64 s0b = fadd2(pk(v[2], v[3]), pk(v[6], v[7]));
+                        const u64 s1a = fadd2(pk(v[1], v[2]), pk(v[3], v[4]));
+                        const u64 s1b = fadd2(pk(v[3], v[4]), pk(v[5], v[6]));
+                        u64 oa = fmul2(pk(v[2], v[3]), G2[2]);
+                        u64 ob = fmul2(pk(v[4], v[5]), G2[2]);
+                        oa = ffma2(s1a, G2[1], oa); ob = ffma2(s1b, G2[1], ob);
+                        oa = ffma2(s0a, G2[0], oa); ob = ffma2(s0b, G2[0], ob);
+                        // D smoothing: slots ph, ph+1, ph+2, ph+3 (mod 4) hold planes z-4 .. z-1
+                        if (emit) {
+                            u64 acc0 = fmul2(win[a][0][ph], G2[0]), acc1 = fmul2(win[a][1][ph], G2[0]);
+#pragma unroll
+                            for (int t = 1; t < NWIN; ++t) {
+                                acc0 = ffma2(win[a][0][(ph + t) % NWIN], G2[t], acc0);
+                                acc1 = ffma2(win[a][1][(ph + t) % NWIN], G2[t], acc1);
+                            }
+                            m[a][0] = ffma2(oa, G2[NT - 1], acc0);
+                            m[a][1] = ffma2(ob, G2[NT - 1], acc1);
+                        }
+                        win[a][0][ph] = oa;
+                        win[a][1][ph] = ob;
+                    }
+                    if (emit) {
+                        float o[3][4];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float x0[2], x1[2], x2[2];
+                            unpk(m[0][j], x0[0], x0[1]); unpk(m[1][j], x1[0], x1[1]); unpk(m[2][j], x2[0], x2[1]);
+                            float mn[2], sc2[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float t = fminf(fminf(x0[e], x1[e]), x2[e]);
+                                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+                                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+                                mn[e] = t;
+                            }
+                            const u64 MN = pk(mn[0], mn[1]);
+                            const u64 m0 = fsub2(m[0][j], MN), m1 = fsub2(m[1][j], MN), m2 = fsub2(m[2][j], MN);   // mind.py:156
+                            u64 S = fadd2(fadd2(m0, m1), m2);
+                            float s[2];
+                            unpk(S, s[0], s[1]);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float t = s[e];
+                                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                                float v = t * (1.f / 12.f);                                   // mind.py:157
+                                if (FIX) {
+                                    v = fminf(fmaxf(v, lo), hi);                               // mind.py:158-160
+                                    sc2[e] = -1.4426950408889634f * rcp_approx(v);
+                                } else {
+                                    if (cg == 0 && valid[2 * j + e]) {
+                                        st_sum += v;
+                                        st_max = fmaxf(st_max, v);
+                                        if (v > 0.f) st_min = fminf(st_min, v);
+                                    }
+                                    // v == 0 <=> all m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
+                                    sc2[e] = v > 0.f ? -1.4426950408889634f * rcp_approx(v) : 0.f;
+                                }
+                            }
+                            const u64 SCL = pk(sc2[0], sc2[1]);
+                            float y0[2], y1[2], y2[2];
+                            unpk(fmul2(m0, SCL), y0[0], y0[1]); unpk(fmul2(m1, SCL), y1[0], y1[1]); unpk(fmul2(m2, SCL), y2[0], y2[1]);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {                                      // mind.py:161-162
+                                o[0][2 * j + e] = ex2_approx(y0[e]);
+                                o[1][2 * j + e] = ex2_approx(y1[e]);
+                                o[2][2 * j + e] = ex2_approx(y2[e]);
+                            }
+                        }
+                        float *op = op0 + (size_t)(d - d0) * HW;
+                        if (aligned16 && valid[3]) {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+                                __stcs(reinterpret_cast<float4 *>(op + a * ch_stride), make_float4(o[a][0], o[a][1], o[a][2], o[a][3]));
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (valid[k]) __stcs(op + a * ch_stride + k, o[a][k]);
+                        }
+                    }
+                }
+            }
+            if (!FIX) {
+                st_sum = warp_sum(st_sum); st_min = warp_min(st_min); st_max = warp_max(st_max);
+                if (lane == 0) { red[0][warp] = st_sum; red[1][warp] = st_min; red[2][warp] = st_max; }
+            }
+        }
+    }
+    if (!FIX) {
+        __syncthreads();
+        if (warp == 0) {
+            float s = lane < C_WARPS ? red[0][lane] : 0.f;
+            float mnv = lane < C_WARPS ? red[1][lane] : __int_as_float(0x7f800000);
+            float mxv = lane < C_WARPS ? red[2][lane] : 0.f;
+            s = warp_sum(s); mnv = warp_min(mnv); mxv = warp_max(mxv);
+            if (lane == 0) stats[nb - 1] = make_float4(s, mnv, mxv, 0.f);
+            // batches this (shorter) chunk never ran: neutral entries
+            for (int i = nb + lane; i < P.nbatch; i += 32) stats[i] = make_float4(0.f, __int_as_float(0x7f800000), 0.f, 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ void decode_cta(const Params &P, int cta, int &b, int &h0, int &w0, int &d0, int &d1)
+{
+    const int cd = cta % P.nCD; cta /= P.nCD;
+    const int tw = cta % P.nTW; cta /= P.nTW;
+    const int th = cta % P.nTH; cta /= P.nTH;
+    b = cta;
+    h0 = th * MIND_TH; w0 = tw * MIND_TW;
+    d0 = cd * P.chunkD;
+    d1 = min(P.D, d0 + P.chunkD);
+}
+
+template <int DELTA, int NOISE>
+__global__ void __launch_bounds__(NTHREADS, 1) mind_fast_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float red[3][C_WARPS];
+    int b, h0, w0, d0, d1;
+    decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
+    process<DELTA, NOISE, false>(P, smem, red, b, h0, w0, d0, d1, 0.f, 0.f, P.stats + (size_t)blockIdx.x * P.nbatch);
+}
+
+// pass 2: persistent CTAs walk the list of (CTA, batch) units whose clamp is active
+template <int DELTA, int NOISE>
+__global__ void __launch_bounds__(NTHREADS, 1) mind_fast_fix_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float red[3][C_WARPS];
+    const int count = P.fix_hdr[0];
+    const float lo = P.fix_lohi[0], hi = P.fix_lohi[1];
+    for (int u = blockIdx.x; u < count; u += gridDim.x) {
+        const int unit = P.fix_hdr[1 + u];
+        const int cta = unit / P.nbatch, n = unit - cta * P.nbatch;
+        int b, h0, w0, d0, d1;
+        decode_cta(P, cta, b, h0, w0, d0, d1);
+        // batch n of pass 1 emitted planes d0 + PB*n - 2R .. + PB-1 (clipped to the chunk)
+        const int lo_d = max(d0, d0 + n * PB - 2 * R), hi_d = min(d1 - 1, d0 + n * PB - 2 * R + PB - 1);
+        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
+        __syncthreads();
+    }
+}
+
+// one CTA: mean_all(v) -> clamp bounds; compact list of units needing pass 2
+__global__ void __launch_bounds__(1024) mind_fast_finalize(const float4 *stats, int nunits, double inv_count, int *fix_hdr,
+                                                           float *fix_lohi)
+{
+    __shared__ double red[32];
+    __shared__ float s_lo, s_hi, s_mean;
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int i = tid; i < nunits; i += 1024) s += (double)stats[i].x;
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    if (tid == 0) fix_hdr[0] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < 32; ++i) tot += red[i];
+        const float mean = (float)(tot * inv_count);
+        s_mean = mean;
+        s_lo = mean * 0.001f;   // mind.py:158-160
+        s_hi = mean * 1000.f;
+        fix_lohi[0] = s_lo; fix_lohi[1] = s_hi;
+    }
+    __syncthreads();
+    const float lo = s_lo, hi = s_hi, mean = s_mean;
+    for (int i = tid; i < nunits; i += 1024) {
+        const float4 st = stats[i];
+        // units that emitted nothing carry {0, inf, 0}
+        const bool touched = st.z > 0.f || st.y < __int_as_float(0x7f800000) || !(mean > 0.f);
+        if (touched && (!(mean > 0.f) || st.z > hi || st.y < lo)) fix_hdr[1 + atomicAdd(&fix_hdr[0], 1)] = i;
+    }
+}
+
+struct Plan {
+    int nTH, nTW, nCD, chunkD, ncta, nbatch;
+};
+
+static Plan make_plan(int B, int D, int H, int W)
+{
+    Plan p;
+    p.nTH = (H + MIND_TH - 1) / MIND_TH;
+    p.nTW = (W + MIND_TW - 1) / MIND_TW;
+    const long base = (long)B * p.nTH * p.nTW;
+    // One CTA per SM is resident.  Choose the number of D chunks that minimises
+    //   waves * (planes marched per CTA, rounded up to whole batches, + fixed per-CTA cost):
+    // splitting D fills idle SMs but every chunk re-marches 2R warm-up planes.
+    const int sms = sm_count();
+    const int max_chunks = (D + 15) / 16;
+    long best_cost = -1;
+    int best = 1;
+    for (int ncd = 1; ncd <= max_chunks; ++ncd) {
+        const int chunk = (D + ncd - 1) / ncd;
+        const int n = (D + chunk - 1) / chunk;
+        const long waves = (base * n + sms - 1) / sms;
+        const long cost = waves * (((chunk + 2 * R + PB - 1) / PB) * PB + 3);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ncd; }
+    }
+    p.chunkD = (D + best - 1) / best;
+    p.nCD = (D + p.chunkD - 1) / p.chunkD;
+    p.ncta = (int)(base * p.nCD);
+    p.nbatch = (p.chunkD + 2 * R + PB - 1) / PB;
+    return p;
+}
+
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+template <int DELTA, int NOISE>
+static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStream_t stream)
+{
+    using G = Geom<DELTA>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mind_fast_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        cudaFuncSetAttribute(mind_fast_fix_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        configured = true;
+    }
+    Params P = P0;
+    const int nunits = plan.ncta * plan.nbatch;
+    char *base = (char *)workspace;
+    P.stats = (float4 *)base;
+    int *hdr = (int *)(base + align16((size_t)nunits * sizeof(float4)));
+    float *lohi = (float *)((char *)hdr + align16((size_t)(nunits + 1) * sizeof(int)));
+    P.fix_hdr = hdr;
+    P.fix_lohi = lohi;
+    mind_fast_kernel<DELTA, NOISE><<<plan.ncta, NTHREADS, G::SMEM, stream>>>(P);
+    int rc = check_launch("mind_fast_kernel");
+    if (rc) return rc;
+    mind_fast_finalize<<<1, 1024, 0, stream>>>(P.stats, nunits, 1.0 / ((double)P.B * P.D * P.H * P.W), hdr, lohi);
+    rc = check_launch("mind_fast_finalize");
+    if (rc) return rc;
+    mind_fast_fix_kernel<DELTA, NOISE><<<sm_count(), NTHREADS, G::SMEM, stream>>>(P);
+    return check_launch("mind_fast_fix_kernel");
+}
+
+template <int DELTA>
+static int launch_noise(const Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
+{
+    if (noise_mode == DGTTA_NOISE_TENSOR) return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
+    return launch<DELTA, DGTTA_NOISE_NONE>(P, plan, workspace, stream);
+}
+
+}  // namespace fast
+
+bool mind_fast_supported(const MindArgs &a)
+{
+    return a.ntaps == fast::NT && a.delta >= 1 && a.delta <= 3 &&
+           (a.noise_mode == DGTTA_NOISE_NONE || a.noise_mode == DGTTA_NOISE_TENSOR);
+}
+
+size_t mind_fast_workspace_bytes(int B, int D, int H, int W)
+{
+    // bound independent of the SM count: chunks are >= 16 planes (or the whole of D)
+    const size_t nTH = (H + MIND_TH - 1) / MIND_TH, nTW = (W + MIND_TW - 1) / MIND_TW;
+    const size_t max_chunks = (D + 15) / 16;
+    // per chunk at most ceil((chunkD + 4)/5) batches with chunkD <= D; bound the product generously
+    const size_t units = (size_t)B * nTH * nTW * ((size_t)D / fast::PB + 3 * max_chunks + 2);
+    return fast::align16(units * sizeof(float4)) + fast::align16((units + 1) * sizeof(int)) + 64;
+}
+
+int mind_fast_launch(const MindArgs &a, cudaStream_t stream)
+{
+    const fast::Plan plan = fast::make_plan(a.B, a.D, a.H, a.W);
+    const size_t nunits = (size_t)plan.ncta * plan.nbatch;
+    const size_t need = fast::align16(nunits * sizeof(float4)) + fast::align16((nunits + 1) * sizeof(int)) + 64;
+    if (a.workspace_bytes < need) {
+        set_error("dgtta_mind_ssc_fwd: workspace too small (%zu < %zu)", a.workspace_bytes, need);
+        return DGTTA_EWORKSPACE;
+    }
+    fast::Params P;
+    P.img = a.img; P.out = a.out; P.noise = a.noise; P.in_scale = a.in_scale;
+    P.stats = nullptr; P.fix_hdr = nullptr; P.fix_lohi = nullptr;
+    P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W;
+    P.nTH = plan.nTH; P.nTW = plan.nTW; P.nCD = plan.nCD; P.chunkD = plan.chunkD; P.nbatch = plan.nbatch;
+    P.rw = a.rw;
+    for (int i = 0; i < fast::NT; ++i) P.taps[i] = a.taps[i];
+    switch (a.delta) {
+        case 1: return fast::launch_noise<1>(P, plan, a.workspace, a.noise_mode, stream);
+        case 2: return fast::launch_noise<2>(P, plan, a.workspace, a.noise_mode, stream);
+        default: return fast::launch_noise<3>(P, plan, a.workspace, a.noise_mode, stream);
+    }
+}
+
+}  // namespace dgtta

@@ -1,373 +1,22 @@
-// MIND-SSC descriptor — fused 3-D stencil for sm_100a.
+// MIND-SSC descriptor - C-ABI entry point (include/dgtta.h).
 //
 // Replaces MIND3D.forward of the reference (dg_tta/mind.py:142-164; shift table :104-136; Gaussian
-// smoothing :5-43).  Math per output voxel p and channel c (SURVEY.md §8a2):
+// smoothing :5-43).  Math per output voxel p and channel c (SURVEY.md section 8a2):
 //     E_c(q)   = I(clamp(q + delta*s1_c)) - I(clamp(q + delta*s2_c)) + rw * N_c(q)
 //     ssd_c(p) = sum_{ijk} g_i g_j g_k E_c^2(clamp(p + (i,j,k) - R))
 //     m_c = ssd_c - min_c ssd_c ;  v = mean_c m_c ;  v <- clamp(v, 0.001*mean_all(v), 1000*mean_all(v))
 //     out_c = exp(-m_c / v)
-//
-// Kernel structure ("plane marching"): one CTA owns a TH x TW patch of the H-W plane and walks along D.
-// For every plane it (S1) evaluates the 12 squared edge channels on the patch plus a halo of R into
-// shared memory, (S2) smooths them along W with register-blocked runs, (S3) smooths along H while
-// reading the thread's own column, and keeps the last 2R+1 in-plane results of its voxel in registers
-// so that the smoothing along D never touches memory.  The 12 outputs of a voxel are finished in
-// registers (min / mean / exp) and streamed out with one coalesced 128-byte row per warp and channel.
-// HBM traffic is the algorithmic minimum: 4 B/voxel read (+halo re-reads served by L1/L2) and
-// 48 B/voxel written.
-//
-// The global mean of v couples all voxels (mind.py:158-160).  Pass 1 writes exp(-m/v) with the clamp
-// assumed inactive and records per tile {sum v, min positive v, max v}; pass 2 (same kernel, FIX=true)
-// reduces those to mean_all(v) and recomputes only tiles in which some v leaves
-// [0.001*mean, 1000*mean] — the result is identical to clamping everywhere.
-#include "common.cuh"
-
-namespace dgtta {
-
-// dg_tta/mind.py:104-136.  The six neighbours, indexed 0..5 = D-,D+,H-,H+,W-,W+; channel c is
-// nb[P1[c]] - nb[P2[c]] (verified against tests/golden/mind_shift_table.npz).
-enum { NB_DM = 0, NB_DP = 1, NB_HM = 2, NB_HP = 3, NB_WM = 4, NB_WP = 5 };
-__host__ __device__ constexpr int mind_p1(int c)
-{
-    constexpr int t[12] = {NB_WM, NB_HM, NB_HM, NB_WP, NB_WP, NB_DP, NB_DP, NB_DP, NB_HP, NB_HP, NB_HP, NB_HP};
-    return t[c];
-}
-__host__ __device__ constexpr int mind_p2(int c)
-{
-    constexpr int t[12] = {NB_DM, NB_DM, NB_WM, NB_DM, NB_HM, NB_WM, NB_HM, NB_WP, NB_DM, NB_WM, NB_WP, NB_DP};
-    return t[c];
-}
-
-constexpr int MIND_TH = 16;
-constexpr int MIND_TW = 32;
-constexpr int MIND_THREADS = MIND_TH * MIND_TW;  // one thread per patch voxel
-constexpr int MIND_RUN = 8;                      // W-pass outputs per task
-
-template <int R>
-struct MindGeom {
-    static constexpr int NT = 2 * R + 1;
-    static constexpr int EH = MIND_TH + 2 * R;
-    static constexpr int EW = MIND_TW + 2 * R;
-    static constexpr int QUADS = (MIND_RUN + 2 * R + 3) / 4;            // float4 loads per W-pass task
-    static constexpr int EWP = (MIND_TW - MIND_RUN) + 4 * QUADS;        // padded row so the last task stays in-row
-    static constexpr int NPOS = (EH * EW + MIND_THREADS - 1) / MIND_THREADS;
-    static constexpr int NTASK = 12 * EH * (MIND_TW / MIND_RUN);
-    static constexpr int E2_FLOATS = 12 * EH * EWP;
-    static constexpr int WS_FLOATS = 12 * EH * MIND_TW;
-    static constexpr size_t SMEM = sizeof(float) * (E2_FLOATS + WS_FLOATS);
-};
-
-struct MindParams {
-    const float *img;
-    float *out;
-    const float *noise;
-    const float *in_scale;
-    float4 *tile_stats;  // per CTA: {sum v, min positive v, max v, -}
-    int B, D, H, W;
-    int delta;
-    int nTH, nTW, nCD, chunkD;
-    int noise_mode;
-    float rw;
-    float taps[9];
-    double inv_count;  // 1 / (B*D*H*W)
-};
-
-template <int R, bool FIX, int NOISE>
-__global__ void __launch_bounds__(MIND_THREADS, 1) mind_ssc_kernel(const __grid_constant__ MindParams P)
-{
-    using G = MindGeom<R>;
-    constexpr int NT = G::NT;
-    extern __shared__ __align__(16) float smem[];
-    float *e2 = smem;                  // [12][EH][EWP]  squared edges of the current plane
-    float *ws = smem + G::E2_FLOATS;   // [12][EH][TW]   after the W pass
-    __shared__ double red_d[MIND_THREADS / 32];
-    __shared__ float red_f[3][MIND_THREADS / 32];
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    int bid = blockIdx.x;
-    const int ntiles = gridDim.x;
-    const int cd = bid % P.nCD; bid /= P.nCD;
-    const int tw = bid % P.nTW; bid /= P.nTW;
-    const int th = bid % P.nTH; bid /= P.nTH;
-    const int b = bid;
-    const int H = P.H, W = P.W, D = P.D;
-    const int HW = H * W;
-
-    float lo = 0.f, hi = 0.f;
-    if (FIX) {
-        // mean_all(v) from the per-tile sums, same order in every CTA -> identical value everywhere
-        double s = 0.0;
-        for (int i = tid; i < ntiles; i += MIND_THREADS) s += (double)P.tile_stats[i].x;
-        s = warp_sum(s);
-        if (lane == 0) red_d[warp] = s;
-        __syncthreads();
-        double tot = 0.0;
-        for (int i = 0; i < MIND_THREADS / 32; ++i) tot += red_d[i];
-        const float mean = (float)(tot * P.inv_count);
-        lo = mean * 0.001f;  // mind.py:158-160
-        hi = mean * 1000.f;
-        const float4 st = P.tile_stats[blockIdx.x];
-        const bool need = !(mean > 0.f) || st.z > hi || st.y < lo;
-        if (!need) return;
-    }
-
-    const int h0 = th * MIND_TH, w0 = tw * MIND_TW;
-    const int d0 = cd * P.chunkD;
-    const int d1 = min(D, d0 + P.chunkD);
-    const float *img = P.img + (size_t)b * D * HW;
-    float sa = 1.f, sc = 1.f;
-    const bool scaled = P.in_scale != nullptr;
-    if (scaled) { sa = P.in_scale[2 * b]; sc = P.in_scale[2 * b + 1]; }
-    const int delta = P.delta;
-
-    // S1 bookkeeping: each thread owns up to NPOS halo positions; offsets are plane-invariant
-    int s1_smem[G::NPOS], o_c[G::NPOS], o_hm[G::NPOS], o_hp[G::NPOS], o_wm[G::NPOS], o_wp[G::NPOS];
-#pragma unroll
-    for (int k = 0; k < G::NPOS; ++k) {
-        const int i = tid + k * MIND_THREADS;
-        if (i < G::EH * G::EW) {
-            const int row = i / G::EW, col = i - row * G::EW;
-            // E^2 outside the volume is E^2 at the clamped position (replicate padding of the smoothing,
-            // mind.py:22), so clamp the centre first and then apply the (clamped) shifts
-            const int gh = clampi(h0 - R + row, 0, H - 1), gw = clampi(w0 - R + col, 0, W - 1);
-            s1_smem[k] = row * G::EWP + col;
-            o_c[k] = gh * W + gw;
-            o_hm[k] = clampi(gh - delta, 0, H - 1) * W + gw;
-            o_hp[k] = clampi(gh + delta, 0, H - 1) * W + gw;
-            o_wm[k] = gh * W + clampi(gw - delta, 0, W - 1);
-            o_wp[k] = gh * W + clampi(gw + delta, 0, W - 1);
-        } else {
-            s1_smem[k] = -1;
-            o_c[k] = o_hm[k] = o_hp[k] = o_wm[k] = o_wp[k] = 0;
-        }
-    }
-
-    float taps[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) taps[t] = P.taps[t];
-
-    const int ty = tid / MIND_TW, tx = tid - ty * MIND_TW;
-    const int vh = h0 + ty, vw = w0 + tx;
-    const bool valid = vh < H && vw < W;
-    float *outp = P.out + ((size_t)b * 12 * D) * HW + (size_t)vh * W + vw;
-
-    float win[12][NT];
-#pragma unroll
-    for (int c = 0; c < 12; ++c)
-#pragma unroll
-        for (int t = 0; t < NT; ++t) win[c][t] = 0.f;
-    float x[12];
-#pragma unroll
-    for (int c = 0; c < 12; ++c) x[c] = 0.f;
-
-    float st_sum = 0.f, st_min = __int_as_float(0x7f800000), st_max = 0.f;
-
-    int prev_zc = -1;
-    const int z_begin = d0 - R, z_end = d1 + R;  // logical planes pushed into the D window
-    for (int zb = z_begin; zb < z_end; zb += NT) {
-#pragma unroll
-        for (int ph = 0; ph < NT; ++ph) {
-            const int z = zb + ph;
-            if (z < z_end) {
-                const int zc = clampi(z, 0, D - 1);
-                if (zc != prev_zc) {  // uniform over the CTA
-                    prev_zc = zc;
-                    // ---------------- S1: squared edges of plane zc on the halo patch
-                    const float *p0 = img + (size_t)zc * HW;
-                    const float *pm = img + (size_t)clampi(zc - delta, 0, D - 1) * HW;
-                    const float *pp = img + (size_t)clampi(zc + delta, 0, D - 1) * HW;
-#pragma unroll
-                    for (int k = 0; k < G::NPOS; ++k) {
-                        if (s1_smem[k] >= 0) {
-                            float nb[6];
-                            nb[NB_DM] = __ldg(pm + o_c[k]);
-                            nb[NB_DP] = __ldg(pp + o_c[k]);
-                            nb[NB_HM] = __ldg(p0 + o_hm[k]);
-                            nb[NB_HP] = __ldg(p0 + o_hp[k]);
-                            nb[NB_WM] = __ldg(p0 + o_wm[k]);
-                            nb[NB_WP] = __ldg(p0 + o_wp[k]);
-                            if (scaled) {
-#pragma unroll
-                                for (int q = 0; q < 6; ++q) nb[q] = __fmul_rn(__fmul_rn(nb[q], sa), sc);
-                            }
-                            float *dst = e2 + s1_smem[k];
-#pragma unroll
-                            for (int c = 0; c < 12; ++c) {
-                                float e = nb[mind_p1(c)] - nb[mind_p2(c)];
-                                if (NOISE == DGTTA_NOISE_TENSOR) {
-                                    const float n = __ldg(P.noise + ((size_t)(b * 12 + c) * D + zc) * HW + o_c[k]);
-                                    e = __fadd_rn(e, __fmul_rn(P.rw, n));  // mind.py:150-152, two roundings
-                                }
-                                dst[c * (G::EH * G::EWP)] = e * e;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    // ---------------- S2: smooth along W, MIND_RUN outputs per task
-                    for (int t = tid; t < G::NTASK; t += MIND_THREADS) {
-                        const int j = t & (MIND_TW / MIND_RUN - 1);
-                        const int cr = t / (MIND_TW / MIND_RUN);  // c * EH + row
-                        const float4 *src = reinterpret_cast<const float4 *>(e2 + cr * G::EWP + j * MIND_RUN);
-                        float v[4 * G::QUADS];
-#pragma unroll
-                        for (int q = 0; q < G::QUADS; ++q) {
-                            const float4 f = src[q];
-                            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
-                        }
-                        float o[MIND_RUN];
-#pragma unroll
-                        for (int k = 0; k < MIND_RUN; ++k) {
-                            float acc = taps[0] * v[k];
-#pragma unroll
-                            for (int tt = 1; tt < NT; ++tt) acc = fmaf(taps[tt], v[k + tt], acc);
-                            o[k] = acc;
-                        }
-                        float4 *dst = reinterpret_cast<float4 *>(ws + cr * MIND_TW + j * MIND_RUN);
-                        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    }
-                    __syncthreads();
-                    // ---------------- S3: smooth along H for the thread's own voxel
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        const float *col = ws + (c * G::EH + ty) * MIND_TW + tx;
-                        float acc = taps[0] * col[0];
-#pragma unroll
-                        for (int tt = 1; tt < NT; ++tt) acc = fmaf(taps[tt], col[tt * MIND_TW], acc);
-                        x[c] = acc;
-                    }
-                    // the next S1 overwrites e2 only after every thread passed the S2 barrier of this plane,
-                    // and the next S2 overwrites ws only after the next S1 barrier, which every thread reaches
-                    // after finishing this S3: no extra barrier needed.
-                }
-                // ---------------- D pass: push x into the register window (slot ph), emit plane z-R
-#pragma unroll
-                for (int c = 0; c < 12; ++c) win[c][ph] = x[c];
-                const int d = z - R;
-                if (d >= d0) {
-                    float ssd[12];
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        float acc = taps[0] * win[c][(ph + 1) % NT];
-#pragma unroll
-                        for (int tt = 1; tt < NT; ++tt) acc = fmaf(taps[tt], win[c][(ph + 1 + tt) % NT], acc);
-                        ssd[c] = acc;
-                    }
-                    float mn = ssd[0];
-#pragma unroll
-                    for (int c = 1; c < 12; ++c) mn = fminf(mn, ssd[c]);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        ssd[c] -= mn;   // mind.py:156
-                        sum += ssd[c];
-                    }
-                    float v = __fdiv_rn(sum, 12.f);  // mind.py:157
-                    float scale;
-                    if (FIX) {
-                        v = fminf(fmaxf(v, lo), hi);  // mind.py:158-160
-                        scale = -1.4426950408889634f * __fdiv_rn(1.f, v);
-                    } else {
-                        if (valid) {
-                            st_sum += v;
-                            st_max = fmaxf(st_max, v);
-                            if (v > 0.f) st_min = fminf(st_min, v);
-                        }
-                        // v == 0 means every m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
-                        scale = v > 0.f ? -1.4426950408889634f * __fdiv_rn(1.f, v) : 0.f;
-                    }
-                    if (valid) {
-                        float *o = outp + (size_t)d * HW;
-#pragma unroll
-                        for (int c = 0; c < 12; ++c)
-                            __stcs(o + (size_t)c * D * HW, ex2_approx(ssd[c] * scale));  // mind.py:161-162
-                    }
-                }
-            }
-        }
-    }
-
-    if (!FIX) {
-        st_sum = warp_sum(st_sum);
-        st_min = warp_min(st_min);
-        st_max = warp_max(st_max);
-        if (lane == 0) { red_f[0][warp] = st_sum; red_f[1][warp] = st_min; red_f[2][warp] = st_max; }
-        __syncthreads();
-        if (tid == 0) {
-            float s = 0.f, mnv = __int_as_float(0x7f800000), mxv = 0.f;
-            for (int i = 0; i < MIND_THREADS / 32; ++i) {
-                s += red_f[0][i];
-                mnv = fminf(mnv, red_f[1][i]);
-                mxv = fmaxf(mxv, red_f[2][i]);
-            }
-            P.tile_stats[blockIdx.x] = make_float4(s, mnv, mxv, 0.f);
-        }
-    }
-}
-
-struct MindPlan {
-    int nTH, nTW, nCD, chunkD, ntiles;
-};
-
-static MindPlan mind_plan(int B, int D, int H, int W)
-{
-    MindPlan p;
-    p.nTH = (H + MIND_TH - 1) / MIND_TH;
-    p.nTW = (W + MIND_TW - 1) / MIND_TW;
-    const long base = (long)B * p.nTH * p.nTW;
-    // one CTA per SM is resident (512 threads, ~65 KB smem): split D so that the grid fills the SMs,
-    // but keep chunks long enough that the 2R warm-up planes stay a small fraction of the work
-    const int sms = sm_count();
-    int ncd = (int)((sms + base - 1) / base);
-    const int max_chunks = (D + 15) / 16;
-    if (ncd > max_chunks) ncd = max_chunks;
-    if (ncd < 1) ncd = 1;
-    p.chunkD = (D + ncd - 1) / ncd;
-    p.nCD = (D + p.chunkD - 1) / p.chunkD;
-    p.ntiles = (int)(base * p.nCD);
-    return p;
-}
-
-template <int R, int NOISE>
-static int mind_launch(const MindParams &P, int ntiles, cudaStream_t stream)
-{
-    using G = MindGeom<R>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(mind_ssc_kernel<R, false, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-        cudaFuncSetAttribute(mind_ssc_kernel<R, true, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-        configured = true;
-    }
-    mind_ssc_kernel<R, false, NOISE><<<ntiles, MIND_THREADS, G::SMEM, stream>>>(P);
-    int rc = check_launch("mind_ssc_kernel<spec>");
-    if (rc) return rc;
-    mind_ssc_kernel<R, true, NOISE><<<ntiles, MIND_THREADS, G::SMEM, stream>>>(P);
-    return check_launch("mind_ssc_kernel<fix>");
-}
-
-template <int R>
-static int mind_dispatch_noise(const MindParams &P, int ntiles, cudaStream_t stream)
-{
-    switch (P.noise_mode) {
-        case DGTTA_NOISE_NONE: return mind_launch<R, DGTTA_NOISE_NONE>(P, ntiles, stream);
-        case DGTTA_NOISE_TENSOR: return mind_launch<R, DGTTA_NOISE_TENSOR>(P, ntiles, stream);
-        default:
-            set_error("dgtta_mind_ssc_fwd: noise_mode %d not supported", P.noise_mode);
-            return DGTTA_EUNSUPPORTED;
-    }
-}
-
-}  // namespace dgtta
+// Two kernels implement it: mind_fast.cu (5 taps, delta <= 3: everything the reference's trainers and
+// TTA use) and mind_general.cu (other tap counts / dilations).
+#include "mind_internal.cuh"
 
 using namespace dgtta;
 
 extern "C" size_t dgtta_mind_workspace_bytes(int B, int D, int H, int W)
 {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-    // upper bound independent of the SM count: at most ceil(D/16) chunks (see mind_plan)
-    const size_t tiles = (size_t)B * ((H + MIND_TH - 1) / MIND_TH) * ((W + MIND_TW - 1) / MIND_TW) * ((D + 15) / 16);
-    return tiles * sizeof(float4);
+    const size_t a = mind_fast_workspace_bytes(B, D, H, W), b = mind_general_workspace_bytes(B, D, H, W);
+    return a > b ? a : b;
 }
 
 extern "C" uint64_t dgtta_mind_philox_offset_increment(int B, int D, int H, int W, int sm_count_, int max_threads_per_sm)
@@ -389,7 +38,7 @@ extern "C" int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const fl
 {
     (void)philox_seed; (void)philox_offset;
     if (!img_dev || !out_dev || !taps_host || !workspace_dev) { set_error("dgtta_mind_ssc_fwd: null pointer"); return DGTTA_ENULL; }
-    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || delta < 1 || ntaps < 1 || ntaps > 9 || !(ntaps & 1)) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || delta < 1 || ntaps < 3 || ntaps > 9 || !(ntaps & 1)) {
         set_error("dgtta_mind_ssc_fwd: bad shape/params B=%d D=%d H=%d W=%d delta=%d ntaps=%d", B, D, H, W, delta, ntaps);
         return DGTTA_EINVAL;
     }
@@ -397,26 +46,18 @@ extern "C" int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const fl
         set_error("dgtta_mind_ssc_fwd: volume too large");
         return DGTTA_EINVAL;
     }
+    if (noise_mode != DGTTA_NOISE_NONE && noise_mode != DGTTA_NOISE_TENSOR) {
+        set_error("dgtta_mind_ssc_fwd: noise_mode %d not supported", noise_mode);
+        return DGTTA_EUNSUPPORTED;
+    }
     if (noise_mode == DGTTA_NOISE_TENSOR && !noise_dev) { set_error("dgtta_mind_ssc_fwd: noise tensor missing"); return DGTTA_ENULL; }
-    const MindPlan plan = mind_plan(B, D, H, W);
-    if (workspace_bytes < (size_t)plan.ntiles * sizeof(float4) || ((uintptr_t)workspace_dev & 15)) {
-        set_error("dgtta_mind_ssc_fwd: workspace too small or misaligned (%zu < %zu)", workspace_bytes,
-                  (size_t)plan.ntiles * sizeof(float4));
-        return DGTTA_EWORKSPACE;
-    }
-    MindParams P;
-    P.img = img_dev; P.out = out_dev; P.noise = noise_dev; P.in_scale = in_scale_dev;
-    P.tile_stats = (float4 *)workspace_dev;
-    P.B = B; P.D = D; P.H = H; P.W = W; P.delta = delta;
-    P.nTH = plan.nTH; P.nTW = plan.nTW; P.nCD = plan.nCD; P.chunkD = plan.chunkD;
-    P.noise_mode = noise_mode; P.rw = randn_weighting;
-    for (int i = 0; i < 9; ++i) P.taps[i] = i < ntaps ? taps_host[i] : 0.f;
-    P.inv_count = 1.0 / ((double)B * D * H * W);
-    switch (ntaps / 2) {
-        case 0: return mind_dispatch_noise<0>(P, plan.ntiles, (cudaStream_t)stream);
-        case 1: return mind_dispatch_noise<1>(P, plan.ntiles, (cudaStream_t)stream);
-        case 2: return mind_dispatch_noise<2>(P, plan.ntiles, (cudaStream_t)stream);
-        case 3: return mind_dispatch_noise<3>(P, plan.ntiles, (cudaStream_t)stream);
-        default: return mind_dispatch_noise<4>(P, plan.ntiles, (cudaStream_t)stream);
-    }
+    if ((uintptr_t)workspace_dev & 15) { set_error("dgtta_mind_ssc_fwd: workspace must be 16-byte aligned"); return DGTTA_EWORKSPACE; }
+    MindArgs a;
+    a.img = img_dev; a.out = out_dev; a.noise = noise_dev; a.in_scale = in_scale_dev;
+    a.workspace = workspace_dev; a.workspace_bytes = workspace_bytes;
+    a.B = B; a.D = D; a.H = H; a.W = W; a.delta = delta; a.ntaps = ntaps;
+    a.noise_mode = noise_mode; a.rw = randn_weighting;
+    for (int i = 0; i < 9; ++i) a.taps[i] = i < ntaps ? taps_host[i] : 0.f;
+    if (mind_fast_supported(a)) return mind_fast_launch(a, (cudaStream_t)stream);
+    return mind_general_launch(a, (cudaStream_t)stream);
 }
