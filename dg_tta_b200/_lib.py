@@ -8,7 +8,10 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdgtta_sm100.so"
+import os
+
+# DGTTA_LIB_PATH lets a developer A/B-test an experimental build of the same CUDA library; there is still no non-CUDA path.
+LIB_PATH = Path(os.environ.get("DGTTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdgtta_sm100.so")
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/dgtta.h one to one (checked by tests/test_abi_symbols.py)

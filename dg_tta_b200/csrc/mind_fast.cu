@@ -29,7 +29,7 @@ constexpr int EH = MIND_TH + 2 * R;   // 20 halo rows
 constexpr int EW = MIND_TW + 2 * R;   // 36 halo columns
 constexpr int TWD = 44;               // tile row pitch: 4 pad + 36 + 4 pad words (conflict-free LDS.128 across rows)
 constexpr int WSP = EW;                    // ws row pitch 36: rows 4 banks apart -> conflict-free LDS/STS.128 across rows
-constexpr int WS_CH = EH * WSP + 8;        // 728: channel pitch == 24 (mod 32) -> the 4 channel groups of a warp hit disjoint banks
+constexpr int WS_CH = EH * WSP + 20;       // 740 words = 185 16-byte chunks == 1 (mod 8): consecutive S2 tasks (9 strips per channel) stay conflict-free
 constexpr int WS_PLANE = 12 * WS_CH;
 constexpr int NQUAD = EW / 4;              // 9 position quads per halo row
 constexpr int S1_TASKS = PB * EH * NQUAD;  // 720
@@ -175,9 +175,11 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 #pragma unroll
     for (int k = 0; k < 4; ++k) valid[k] = row_ok && (vw + k < W);
     // per-channel output pointers of the thread's 4-voxel run, advanced plane by plane
-    float *op0 = P.out + (((size_t)b * 12 + 3 * cg) * D + d0) * HW + (size_t)vh * W + vw;
+    // running output pointer of the thread's 4-voxel run (channel 3*cg), advanced by one plane per emit
+    float *op = P.out + (((size_t)b * 12 + 3 * cg) * D + d0) * HW + (size_t)vh * W + vw;
     const size_t ch_stride = (size_t)D * HW;
-    const bool aligned16 = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && ((W & 3) == 0);
+    const bool vec_store = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && ((W & 3) == 0) && valid[3];
+    const bool stat_lane = cg == 0;
 
     u64 win[3][2][NWIN];   // the last 4 W-smoothed planes of the thread's 4 voxels x 3 channels
 #pragma unroll
@@ -274,20 +276,21 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         // ================= S2: H smoothing of a 4-column strip, in place, sliding 5-row register window
         if (s2_active && zb + s2_pz < z_end) {
             float *col = ws + s2_off;
-            u64 x[NT][2];
+            u64 acc[NT][2];   // partial sums of the 5 output rows that input row r contributes to
 #pragma unroll
             for (int r = 0; r < EH; ++r) {
-                ld4p(col + r * WSP, x[r % NT][0], x[r % NT][1]);
-                if (r >= NT - 1) {
-                    const int o = r - (NT - 1);
-                    u64 a0 = fmul2(x[o % NT][0], G2[0]), a1 = fmul2(x[o % NT][1], G2[0]);
+                u64 x0, x1;
+                ld4p(col + r * WSP, x0, x1);
+                // out_o = sum_t g_t x[o+t]: row r feeds o = r-t with tap t; ascending t per output = ascending rows
 #pragma unroll
-                    for (int t = 1; t < NT; ++t) {
-                        a0 = ffma2(x[(o + t) % NT][0], G2[t], a0);
-                        a1 = ffma2(x[(o + t) % NT][1], G2[t], a1);
-                    }
-                    st4p(col + o * WSP, a0, a1);   // row o is dead as an input from here on
+                for (int t = 0; t < NT; ++t) {
+                    const int o = r - t;
+                    if (o < 0 || o >= MIND_TH) continue;
+                    if (t == 0) { acc[o % NT][0] = fmul2(x0, G2[0]); acc[o % NT][1] = fmul2(x1, G2[0]); }
+                    else { acc[o % NT][0] = ffma2(x0, G2[t], acc[o % NT][0]); acc[o % NT][1] = ffma2(x1, G2[t], acc[o % NT][1]); }
                 }
+                const int done = r - (NT - 1);
+                if (done >= 0) st4p(col + done * WSP, acc[done % NT][0], acc[done % NT][1]);   // row `done` is dead as an input
             }
         }
         __syncthreads();   // ws complete; tiles no longer read in this batch
@@ -301,10 +304,12 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 #pragma unroll
             for (int ph = 0; ph < PB; ++ph) {
                 const int z = zb + ph;
-                if (z < z_end) {
+                {
+                    // No branch around a plane: planes past z_end (tail of the last batch) read stale but finite ws
+                    // data and are never emitted, so the four plane steps form one straight-line block that the
+                    // scheduler can overlap (loads / W pass of plane p+1 under the shuffle+MUFU chain of plane p).
                     const float *wsp = ws + ph * WS_PLANE + c_off;
-                    const int d = z - R;
-                    const bool emit = d >= d0;   // uniform
+                    const bool emit = (z - R) >= d0 && z < z_end;   // uniform
                     u64 m[3][2];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
@@ -314,87 +319,84 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                         // o_k = g2 v[k+2] + g1 (v[k+1] + v[k+3]) + g0 (v[k] + v[k+4]),  k = 0..3, two lanes at a time
                         const u64 s0a = fadd2(pk(v[0], v[1]), pk(v[4], v[5]));
                         const u64 s0b = fadd2(pk(v[2], v[3]), pk(v[6], v[7]));
-                        const u64 s1a = fadd2(pk(v[1], v[2]), pk(v[3], v[4]));
-                        const u64 s1b = fadd2(pk(v[3], v[4]), pk(v[5], v[6]));
+                        const u64 s1a = pk(v[1] + v[3], v[2] + v[4]);
+                        const u64 s1b = pk(v[3] + v[5], v[4] + v[6]);
                         u64 oa = fmul2(pk(v[2], v[3]), G2[2]);
                         u64 ob = fmul2(pk(v[4], v[5]), G2[2]);
                         oa = ffma2(s1a, G2[1], oa); ob = ffma2(s1b, G2[1], ob);
                         oa = ffma2(s0a, G2[0], oa); ob = ffma2(s0b, G2[0], ob);
                         // D smoothing: slots ph, ph+1, ph+2, ph+3 (mod 4) hold planes z-4 .. z-1
-                        if (emit) {
-                            u64 acc0 = fmul2(win[a][0][ph], G2[0]), acc1 = fmul2(win[a][1][ph], G2[0]);
+                        u64 acc0 = fmul2(win[a][0][ph], G2[0]), acc1 = fmul2(win[a][1][ph], G2[0]);
 #pragma unroll
-                            for (int t = 1; t < NWIN; ++t) {
-                                acc0 = ffma2(win[a][0][(ph + t) % NWIN], G2[t], acc0);
-                                acc1 = ffma2(win[a][1][(ph + t) % NWIN], G2[t], acc1);
-                            }
-                            m[a][0] = ffma2(oa, G2[NT - 1], acc0);
-                            m[a][1] = ffma2(ob, G2[NT - 1], acc1);
+                        for (int t = 1; t < NWIN; ++t) {
+                            acc0 = ffma2(win[a][0][(ph + t) % NWIN], G2[t], acc0);
+                            acc1 = ffma2(win[a][1][(ph + t) % NWIN], G2[t], acc1);
                         }
+                        m[a][0] = ffma2(oa, G2[NT - 1], acc0);
+                        m[a][1] = ffma2(ob, G2[NT - 1], acc1);
                         win[a][0][ph] = oa;
                         win[a][1][ph] = ob;
                     }
-                    if (emit) {
-                        float o[3][4];
+                    float o[3][4];
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            float x0[2], x1[2], x2[2];
-                            unpk(m[0][j], x0[0], x0[1]); unpk(m[1][j], x1[0], x1[1]); unpk(m[2][j], x2[0], x2[1]);
-                            float mn[2], sc2[2];
+                    for (int j = 0; j < 2; ++j) {
+                        float x0[2], x1[2], x2[2];
+                        unpk(m[0][j], x0[0], x0[1]); unpk(m[1][j], x1[0], x1[1]); unpk(m[2][j], x2[0], x2[1]);
+                        float mn[2], sc2[2];
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                float t = fminf(fminf(x0[e], x1[e]), x2[e]);
-                                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 8));
-                                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 16));
-                                mn[e] = t;
-                            }
-                            const u64 MN = pk(mn[0], mn[1]);
-                            const u64 m0 = fsub2(m[0][j], MN), m1 = fsub2(m[1][j], MN), m2 = fsub2(m[2][j], MN);   // mind.py:156
-                            u64 S = fadd2(fadd2(m0, m1), m2);
-                            float s[2];
-                            unpk(S, s[0], s[1]);
+                        for (int e = 0; e < 2; ++e) {
+                            float t = fminf(fminf(x0[e], x1[e]), x2[e]);
+                            t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+                            t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+                            mn[e] = t;
+                        }
+                        const u64 MN = pk(mn[0], mn[1]);
+                        const u64 m0 = fsub2(m[0][j], MN), m1 = fsub2(m[1][j], MN), m2 = fsub2(m[2][j], MN);   // mind.py:156
+                        const u64 S = fadd2(fadd2(m0, m1), m2);
+                        float s[2];
+                        unpk(S, s[0], s[1]);
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                float t = s[e];
-                                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                                t += __shfl_xor_sync(0xffffffffu, t, 16);
-                                float v = t * (1.f / 12.f);                                   // mind.py:157
-                                if (FIX) {
-                                    v = fminf(fmaxf(v, lo), hi);                               // mind.py:158-160
-                                    sc2[e] = -1.4426950408889634f * rcp_approx(v);
-                                } else {
-                                    if (cg == 0 && valid[2 * j + e]) {
-                                        st_sum += v;
-                                        st_max = fmaxf(st_max, v);
-                                        if (v > 0.f) st_min = fminf(st_min, v);
-                                    }
-                                    // v == 0 <=> all m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
-                                    sc2[e] = v > 0.f ? -1.4426950408889634f * rcp_approx(v) : 0.f;
-                                }
-                            }
-                            const u64 SCL = pk(sc2[0], sc2[1]);
-                            float y0[2], y1[2], y2[2];
-                            unpk(fmul2(m0, SCL), y0[0], y0[1]); unpk(fmul2(m1, SCL), y1[0], y1[1]); unpk(fmul2(m2, SCL), y2[0], y2[1]);
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {                                      // mind.py:161-162
-                                o[0][2 * j + e] = ex2_approx(y0[e]);
-                                o[1][2 * j + e] = ex2_approx(y1[e]);
-                                o[2][2 * j + e] = ex2_approx(y2[e]);
+                        for (int e = 0; e < 2; ++e) {
+                            float t = s[e];
+                            t += __shfl_xor_sync(0xffffffffu, t, 8);
+                            t += __shfl_xor_sync(0xffffffffu, t, 16);
+                            float v = t * (1.f / 12.f);                                   // mind.py:157
+                            if (FIX) {
+                                v = fminf(fmaxf(v, lo), hi);                               // mind.py:158-160
+                                sc2[e] = -1.4426950408889634f * rcp_approx(v);
+                            } else {
+                                const bool cnt = stat_lane && emit && valid[2 * j + e];
+                                st_sum += cnt ? v : 0.f;
+                                st_max = fmaxf(st_max, cnt ? v : 0.f);
+                                st_min = fminf(st_min, (cnt && v > 0.f) ? v : __int_as_float(0x7f800000));
+                                // v == 0 <=> all m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
+                                sc2[e] = v > 0.f ? -1.4426950408889634f * rcp_approx(v) : 0.f;
                             }
                         }
-                        float *op = op0 + (size_t)(d - d0) * HW;
-                        if (aligned16 && valid[3]) {
+                        const u64 SCL = pk(sc2[0], sc2[1]);
+                        float y0[2], y1[2], y2[2];
+                        unpk(fmul2(m0, SCL), y0[0], y0[1]); unpk(fmul2(m1, SCL), y1[0], y1[1]); unpk(fmul2(m2, SCL), y2[0], y2[1]);
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
-                                __stcs(reinterpret_cast<float4 *>(op + a * ch_stride), make_float4(o[a][0], o[a][1], o[a][2], o[a][3]));
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (valid[k]) __stcs(op + a * ch_stride + k, o[a][k]);
+                        for (int e = 0; e < 2; ++e) {                                      // mind.py:161-162
+                            o[0][2 * j + e] = ex2_approx(y0[e]);
+                            o[1][2 * j + e] = ex2_approx(y1[e]);
+                            o[2][2 * j + e] = ex2_approx(y2[e]);
                         }
                     }
+                    if (vec_store) {
+                        if (emit) {
+                            __stcs(reinterpret_cast<float4 *>(op), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+                            __stcs(reinterpret_cast<float4 *>(op + ch_stride), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+                            __stcs(reinterpret_cast<float4 *>(op + 2 * ch_stride), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
+                        }
+                    } else if (emit) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (valid[k]) __stcs(op + a * ch_stride + k, o[a][k]);
+                    }
+                    op += emit ? HW : 0;
                 }
             }
             if (!FIX) {
