@@ -158,6 +158,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
     u64 SA = pk(1.f, 1.f), SC = SA;
     if (scaled) { SA = pk(P.in_scale[2 * b], P.in_scale[2 * b]); SC = pk(P.in_scale[2 * b + 1], P.in_scale[2 * b + 1]); }
     const u64 RW = pk(P.rw, P.rw);
+    const bool noise_vec = (NOISE == DGTTA_NOISE_TENSOR) && ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.noise) & 7) == 0);
 
     // ---- S2 bookkeeping: one (plane, channel, column quad) task per thread, exactly one round
     const bool s2_active = tid < S2_TASKS;
@@ -251,24 +252,47 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                     for (int j = 0; j < 2; ++j) nbv[a][j] = fmul2(fmul2(nbv[a][j], SA), SC);
             }
             float *wsp = ws + pz * WS_PLANE + r * WSP + 4 * q;
-            const float *nz = nullptr;
-            int ngw[4];
             if (NOISE == DGTTA_NOISE_TENSOR) {
-                nz = P.noise + ((size_t)b * 12 * D + zc) * HW + (size_t)clampi(h0 - R + r, 0, H - 1) * W;
+                // noise of the (clamped) positions: mind.py:150-152 adds rw*N to the edge before squaring; halo
+                // positions outside the volume reuse the sample of the clamped position (they replicate E^2)
+                const float *nz = P.noise + ((size_t)b * 12 * D + zc) * HW + (size_t)clampi(h0 - R + r, 0, H - 1) * W;
+                const int gw0 = w0 - R + 4 * q;
+                const bool interior = gw0 >= 0 && gw0 + 3 < W && noise_vec;   // uniform per task, 8-byte aligned pairs
+                int ngw[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ngw[k] = clampi(w0 - R + 4 * q + k, 0, W - 1);
-            }
+                for (int k = 0; k < 4; ++k) ngw[k] = clampi(gw0 + k, 0, W - 1);
 #pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
-                u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
-                if (NOISE == DGTTA_NOISE_TENSOR) {
-                    const float *np = nz + (size_t)c * D * HW;
-                    // mind.py:150-152: edge + rw * noise, product and sum rounded separately
-                    e0 = fadd2(e0, fmul2(RW, pk(__ldg(np + ngw[0]), __ldg(np + ngw[1]))));
-                    e1 = fadd2(e1, fmul2(RW, pk(__ldg(np + ngw[2]), __ldg(np + ngw[3]))));
+                for (int half = 0; half < 2; ++half) {
+                    u64 n0[6], n1[6];   // six channels in flight at a time
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) {
+                        const float *np = nz + (size_t)(6 * half + cc) * D * HW;
+                        if (interior) {
+                            const float2 a = __ldg(reinterpret_cast<const float2 *>(np + gw0));
+                            const float2 bq = __ldg(reinterpret_cast<const float2 *>(np + gw0 + 2));
+                            n0[cc] = pk(a.x, a.y); n1[cc] = pk(bq.x, bq.y);
+                        } else {
+                            n0[cc] = pk(__ldg(np + ngw[0]), __ldg(np + ngw[1]));
+                            n1[cc] = pk(__ldg(np + ngw[2]), __ldg(np + ngw[3]));
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) {
+                        const int c = 6 * half + cc;
+                        u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
+                        u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
+                        e0 = fadd2(e0, fmul2(RW, n0[cc]));   // product and sum rounded separately, like the reference
+                        e1 = fadd2(e1, fmul2(RW, n1[cc]));
+                        st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
+                    }
                 }
-                st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
+                    const u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
+                    st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
+                }
             }
         }
         __syncthreads();
@@ -296,7 +320,22 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         __syncthreads();   // ws complete; tiles no longer read in this batch
 
         // prefetch the image planes of the next batch while C runs
-        if (n + 1 < nb) load_until(clampi(zb + 2 * PB - 1, 0, D - 1) + DELTA);
+        if (n + 1 < nb) {
+            load_until(clampi(zb + 2 * PB - 1, 0, D - 1) + DELTA);
+            if (NOISE == DGTTA_NOISE_TENSOR) {
+                // pull the next batch's noise rows (144 B each) into L2 so that S1's loads do not pay DRAM latency
+                for (int i = tid; i < 12 * PB * EH; i += NTHREADS) {
+                    const int c = i / (PB * EH), rem = i - c * (PB * EH);
+                    const int pz = rem / EH, r = rem - pz * EH;
+                    const int zn = zb + PB + pz;
+                    if (zn >= z_end) continue;
+                    const float *np = P.noise + (((size_t)b * 12 + c) * D + clampi(zn, 0, D - 1)) * HW +
+                                      (size_t)clampi(h0 - R + r, 0, H - 1) * W + max(w0 - R, 0);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(np + min(32, W - 1 - max(w0 - R, 0))));
+                }
+            }
+        }
 
         // ================= C: W smoothing, D window, MIND normalisation, store
         float st_sum = 0.f, st_min = __int_as_float(0x7f800000), st_max = 0.f;

@@ -82,9 +82,33 @@ def affine_grid_sample(input, theta, out_size=None, mode="bilinear", padding_mod
     return _AffineSample.apply(input, theta, size, _INTERP[mode], _PAD[padding_mode])
 
 
+_SIDE_STREAMS = {}
+
+
 def gin_mind_aug(input):
-    """augmentation_utils.py:173-174: MIND3D()(gin_aug(input)).  GIN's final rescale is deferred
-    into MIND's loads (one pass over the volume less); the values MIND sees are bit-identical to the
-    unfused chain because the same two multiplications are applied in the same order."""
-    mixed, scale = GINGroupConv(dict(_GIN_CFG))(input, defer_scale=True)
-    return mind_ssc(mixed, in_scale=scale)
+    """augmentation_utils.py:173-174: MIND3D()(gin_aug(input)).
+
+    * GIN's final rescale is deferred into MIND's loads (one pass over the volume less); the values MIND sees are
+      bit-identical to the unfused chain because the same two multiplications are applied in the same order.
+    * The N(0,1) field MIND adds to the edges (mind.py:150) does not depend on GIN, so it is drawn on a side stream
+      while the GIN kernels run.  The generator is consumed in the reference's host order (GIN alphas first, then the
+      MIND noise), so the values are the ones `gin_aug` followed by `MIND3D()` would draw."""
+    _lib.require_cuda_f32(input, "input")
+    if input.dim() != 5 or input.shape[1] != 1:
+        raise ValueError(f"gin_mind_aug expects [B,1,D,H,W], got {tuple(input.shape)}")
+    net = GINGroupConv(dict(_GIN_CFG))
+    alphas, kers, shifts = net.draw(input)                    # host draws + device rand(B), reference order
+    B, _, D, H, W = input.shape
+    dev = input.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    side.wait_stream(main)                                    # generator/allocator ordering with earlier work
+    with torch.cuda.stream(side):
+        noise = torch.randn((B, 12, D, H, W), device=dev, dtype=torch.float32)
+    from ..gin import gin_forward
+    mixed, scale = gin_forward(input, kers, shifts, alphas, net.interm_channel, defer_scale=True)
+    main.wait_stream(side)
+    noise.record_stream(main)
+    return mind_ssc(mixed, noise=noise, in_scale=scale)
