@@ -182,6 +182,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.lib().dgtta_launch_count()
     t0.record()
     out = None
     for i in range(args.steps):
@@ -189,6 +190,7 @@ def run_ours(args, rank, world, local_rank):
     t1.record()
     sync_all()
     ms = t0.elapsed_time(t1)
+    launches = _lib.lib().dgtta_launch_count() - launches0   # counted inside libdgtta_sm100.so
     del out
 
     # ---- roofline leg: the dominant launch (MIND-SSC with the noise field streamed in) timed alone with CUDA events
@@ -271,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": vox_step * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-        "gpu_launches": args.steps * 8,   # per step: 4 GIN layers + GIN norm + MIND main/finalize/fix-up (torch.randn not counted)
+        "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (torch.randn's launch not counted)
         "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1,noise=tensor> (+finalize, fix-up)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
@@ -283,12 +285,74 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_tta(args, rank, world, local_rank):
+    """BASELINE configs 3/5: TTA inner steps/s (one accumulation iteration of dg_tta/tta/tta.py:221-275 per step,
+    AdamW step every 16) on a stand-in PlainConvUNet-shaped network with random weights, patch 128^3, batch 2,
+    one synthetic MR-like volume per GPU.  The backbone is PyTorch/cuDNN and out of scope; the transforms are ours."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "tools"))
+    import tta_standin as ts
+    from dg_tta_b200 import _lib
+    _lib.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    patch, batch = [128, 128, 128], 2
+    vol = [synth_volume((1, 1, 231, 228, 242), 5000 + rank)[0].to(dev)]
+    tr = ts.DropInTransforms()
+    model = ts.build_model(tr, num_classes=105, seed=rank).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    idx = list(range(1, 15))
+    rng = np.random.RandomState(rank)
+
+    def step(i):
+        loss = ts.tta_inner_step(model, vol, patch, batch, idx, tr, rng=rng)
+        if (i + 1) % 16 == 0:
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        return loss
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = _lib.lib().dgtta_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms = float(ms[0])
+    print(json.dumps({
+        "metric": "TTA inner steps/s (stand-in loop)", "value": world * args.steps / (ms * 1e-3), "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "stand-in TTA inner step: get_batch -> 2x(affine warp, mind_hook -> PlainConvUNet-shaped "
+                               "fixture 12->105 ch, channel select 14, inverse warp) -> soft-Dice consistency -> backward; "
+                               "patch 128^3, batch 2, one 231x228x242 volume per GPU", "parallelism": f"{world} replicas"},
+        "gpu_launches": int(_lib.lib().dgtta_launch_count() - launches0), "loss": float(loss),
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="transform", choices=["transform", "tta"],
+                    help="transform (default, the bench contract): gin_mind_aug on 2x1x192^3; tta: stand-in TTA inner steps "
+                         "(BASELINE configs 3/5: GIN_MIND transforms feeding a PlainConvUNet-shaped fixture, one volume per GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -306,7 +370,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "tta":
+            run_tta(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -18,6 +18,7 @@ _lib = None
 SIGNATURES = {
     "dgtta_abi_version": (c_int, []),
     "dgtta_last_error": (c_char_p, []),
+    "dgtta_launch_count": (c_uint64, []),
     "dgtta_mind_workspace_bytes": (c_size_t, [c_int] * 4),
     "dgtta_mind_ssc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                    c_float, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),

@@ -15,6 +15,10 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count()
 {
     static int cached[64] = {0};
@@ -30,5 +34,7 @@ int sm_count()
 
 }  // namespace dgtta
 
+namespace dgtta { unsigned long long launches(); }
+extern "C" uint64_t dgtta_launch_count(void) { return dgtta::launches(); }
 extern "C" int dgtta_abi_version(void) { return DGTTA_ABI_VERSION; }
 extern "C" const char *dgtta_last_error(void) { return dgtta::g_err; }

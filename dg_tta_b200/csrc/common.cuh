@@ -11,8 +11,12 @@ namespace dgtta {
 // thread-local error text behind dgtta_last_error()
 void set_error(const char *fmt, ...);
 
+// number of kernels this library has launched in the process (bench.py reports it as gpu_launches)
+void count_launch();
+
 inline int check_launch(const char *what)
 {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

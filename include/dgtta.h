@@ -45,6 +45,8 @@ typedef struct CUstream_st *dgtta_stream_t; /* == cudaStream_t */
 
 int dgtta_abi_version(void);
 const char *dgtta_last_error(void);
+/* kernels launched by this library since the process started (diagnostics; bench.py's gpu_launches) */
+uint64_t dgtta_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * MIND-SSC descriptor.  Replaces MIND3D.forward (dg_tta/mind.py:142-164) including the shift

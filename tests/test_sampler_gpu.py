@@ -95,3 +95,26 @@ def test_gin_mind_aug_fused_chain():
     from dg_tta_b200.tta.augmentation_utils import gin_mind_aug
     res = gin_mind_aug(cuda(g["x"]))
     assert tuple(res.shape) == tuple(g["out"].shape) and not torch.isnan(res).any()
+
+
+def test_get_batch_matches_reference_crops():
+    """torch_utils.get_batch (dg_tta/tta/torch_utils.py:13-76): random, centre and larger-than-volume crops."""
+    from dg_tta_b200.tta.torch_utils import get_batch
+    g = load_golden("get_batch")
+    sample = torch.from_numpy(g["sample"])
+    patch = g["patch"].tolist()
+    torch.manual_seed(int(g["seed"]))
+    b_img, b_lbl = get_batch([sample], [0, 0], patch, fixed_patch_idx=None, device="cuda")
+    for got, ref in ((b_img[0], g["img0"]), (b_img[1], g["img1"])):
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-5
+    for got, ref in ((b_lbl[0], g["lbl0"]), (b_lbl[1], g["lbl1"])):
+        assert got.dtype == torch.int64 and (got.cpu().numpy() != ref).mean() <= 0.002
+    c_img, c_lbl = get_batch([sample.cuda()], [0], patch, fixed_patch_idx="center", device="cuda")
+    assert np.abs(c_img[0].cpu().numpy() - g["img_c"]).max() <= 2e-5
+    assert (c_lbl[0].cpu().numpy() != g["lbl_c"]).mean() <= 0.002
+    torch.manual_seed(int(g["seed_large"]))
+    l_img, l_lbl = get_batch([sample], [0], g["patch_large"].tolist(), device="cuda")
+    assert np.abs(l_img[0].cpu().numpy() - g["img_l"]).max() <= 2e-5
+    assert (l_lbl[0].cpu().numpy() != g["lbl_l"]).mean() <= 0.002
+    img_only, none_lbl = get_batch([sample[:1]], [0], patch, fixed_patch_idx="center", device="cuda")
+    assert none_lbl[0] is None and tuple(img_only[0].shape) == (1, 1, *patch)
