@@ -1,0 +1,25 @@
+#!/bin/bash
+# Run on the GPU box (via gpurun): captures the evidence that tools/collect_profiles.py turns into profiles/.
+#   tools/make_profiles.sh <round-tag>
+tag=${1:-r01}
+mkdir -p gpurun_out
+# 1. every launch of the bench command with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches_bench.csv \
+    python bench.py --steps 3 --warmup 3 > gpurun_out/${tag}_bench_under_ncu.log 2>&1
+# 2. full sections for the hot kernels (one capture each; -lineinfo sources imported)
+ncu --set full --clock-control none --import-source on -k regex:"mind_fast_kernel" -s 2 -c 1 -o gpurun_out/${tag}_mind_noise \
+    python tools/prof_mind.py mind_noise > gpurun_out/${tag}_ncu_mind_noise.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mind_fast_kernel" -s 2 -c 1 -o gpurun_out/${tag}_mind_clean \
+    python tools/prof_mind.py mind > gpurun_out/${tag}_ncu_mind_clean.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gin_conv_seg_kernel" -s 8 -c 4 -o gpurun_out/${tag}_gin3333 \
+    python tools/prof_mind.py gin3333 > gpurun_out/${tag}_ncu_gin.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"affine_sample" -c 4 -o gpurun_out/${tag}_sampler \
+    python tools/prof_mind.py sampler > gpurun_out/${tag}_ncu_sampler.log 2>&1
+# 3. the numbers themselves (never taken under a profiler)
+python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err
+python bench.py --workload tta --steps 16 --warmup 3 > gpurun_out/${tag}_bench_tta.json 2>> gpurun_out/${tag}_bench.err
+python tools/kernel_times.py > gpurun_out/${tag}_kernel_times.txt 2>&1
+python tests/perf_eager_gpu.py > gpurun_out/${tag}_eager_vs_ours.json 2>> gpurun_out/${tag}_bench.err
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${tag}_nvidia_smi.csv
+ls -la gpurun_out | tail -20

@@ -34,4 +34,13 @@ elif what.startswith("gin"):
         seed += 1
     for _ in range(3):
         gin_forward(x, kers, shifts, alphas, 2)
+elif what == "sampler":
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine
+    torch.manual_seed(0)
+    R, Ri = get_rand_affine(2)
+    img = synth_volume((2, 1, 128, 128, 128), 3).cuda()
+    affine_grid_sample(img, R, padding_mode="border")
+    lg = torch.randn(2, 14, 128, 128, 128, device="cuda", requires_grad=True)
+    out = affine_grid_sample(lg, Ri)
+    out.backward(torch.randn_like(out))
 torch.cuda.synchronize()
