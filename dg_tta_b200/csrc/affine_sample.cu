@@ -39,10 +39,33 @@ struct Coords {
     float ix, iy, iz;
 };
 
-template <int PAD>
-__device__ __forceinline__ Coords source_coords(const SampleParams &P, const float *th, int d, int h, int w)
+// Block = 32 (w) x 8 (h) output voxels of one d-plane; the per-axis base coordinates (two IEEE divisions each)
+// are tabulated once per block in shared memory instead of being recomputed per voxel.
+constexpr int SBX = 32, SBY = 8;
+constexpr int SAMPLE_THREADS = SBX * SBY;
+
+struct BlockCoords {
+    float th[12];
+    float bx[SBX];
+    float by[SBY];
+    float bz;
+};
+
+__device__ __forceinline__ void block_setup(const SampleParams &P, BlockCoords &S, int b, int w0, int h0, int d)
 {
-    const float xn = base_coord(w, P.Wo), yn = base_coord(h, P.Ho), zn = base_coord(d, P.Do);
+    const int t = threadIdx.y * SBX + threadIdx.x;
+    if (t < 12) S.th[t] = P.theta[b * 12 + t];
+    if (t >= 32 && t < 32 + SBX) S.bx[t - 32] = base_coord(min(w0 + t - 32, P.Wo - 1), P.Wo);
+    if (t >= 64 && t < 64 + SBY) S.by[t - 64] = base_coord(min(h0 + t - 64, P.Ho - 1), P.Ho);
+    if (t == 96) S.bz = base_coord(d, P.Do);
+    __syncthreads();
+}
+
+template <int PAD>
+__device__ __forceinline__ Coords source_coords(const SampleParams &P, const BlockCoords &S)
+{
+    const float *th = S.th;
+    const float xn = S.bx[threadIdx.x], yn = S.by[threadIdx.y], zn = S.bz;
     // row-times-column products summed left to right, like the reference's base_grid @ theta^T
     const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[0], xn), __fmul_rn(th[1], yn)), __fmul_rn(th[2], zn)), th[3]);
     const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[4], xn), __fmul_rn(th[5], yn)), __fmul_rn(th[6], zn)), th[7]);
@@ -53,54 +76,78 @@ __device__ __forceinline__ Coords source_coords(const SampleParams &P, const flo
     return c;
 }
 
-constexpr int SAMPLE_THREADS = 256;
+struct Corners {
+    float wgt[8];
+    int off[8];   // element offset inside one channel volume, -1 = outside (zeros padding)
+};
 
-// one thread per output voxel; channels looped inside so coordinates and weights are computed once
+__device__ __forceinline__ Corners trilinear_corners(const SampleParams &P, const Coords &c)
+{
+    const float fx = floorf(c.ix), fy = floorf(c.iy), fz = floorf(c.iz);
+    const float tx = c.ix - fx, ty = c.iy - fy, tz = c.iz - fz;
+    // clamp before the int conversion so that wild coordinates cannot overflow
+    const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)P.Wi), y0 = (int)fminf(fmaxf(fy, -2.f), (float)P.Hi),
+              z0 = (int)fminf(fmaxf(fz, -2.f), (float)P.Di);
+    Corners q;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+        const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+        const bool ok = xx >= 0 && xx < P.Wi && yy >= 0 && yy < P.Hi && zz >= 0 && zz < P.Di;
+        q.wgt[k] = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+        q.off[k] = ok ? (zz * P.Hi + yy) * P.Wi + xx : -1;
+    }
+    return q;
+}
+
+// grid: x = w-tiles * h-tiles, y = d, z = b.  Channels are looped inside (4 at a time: 32 independent gathers in
+// flight) so that coordinates and weights are computed once per voxel.
 template <int INTERP, int PAD>
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const __grid_constant__ SampleParams P)
 {
+    __shared__ BlockCoords S;
+    const int ntw = (P.Wo + SBX - 1) / SBX;
+    const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
+    const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
+    block_setup(P, S, b, w0, h0, d);
+    const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
+    if (w >= P.Wo || h >= P.Ho) return;
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
-    const int b = blockIdx.y;
-    __shared__ float th[12];
-    if (threadIdx.x < 12) th[threadIdx.x] = P.theta[b * 12 + threadIdx.x];
-    __syncthreads();
-    for (size_t p = (size_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x; p < Vo; p += (size_t)gridDim.x * SAMPLE_THREADS) {
-        const int w = (int)(p % P.Wo);
-        const int h = (int)((p / P.Wo) % P.Ho);
-        const int d = (int)(p / ((size_t)P.Wo * P.Ho));
-        const Coords c = source_coords<PAD>(P, th, d, h, w);
-        const float *src = P.in + (size_t)b * P.C * Vi;
-        float *dst = P.out + (size_t)b * P.C * Vo + p;
-        if (INTERP == DGTTA_INTERP_NEAREST) {
-            const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
-            const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
-            const size_t off = ok ? ((size_t)(int)rz * P.Hi + (int)ry) * P.Wi + (int)rx : 0;
-            for (int ch = 0; ch < P.C; ++ch) __stcs(dst + ch * Vo, ok ? __ldg(src + ch * Vi + off) : 0.f);
-        } else {
-            const float fx = floorf(c.ix), fy = floorf(c.iy), fz = floorf(c.iz);
-            const float tx = c.ix - fx, ty = c.iy - fy, tz = c.iz - fz;
-            // clamp before the int conversion so that wild coordinates cannot overflow
-            const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)P.Wi), y0 = (int)fminf(fmaxf(fy, -2.f), (float)P.Hi),
-                      z0 = (int)fminf(fmaxf(fz, -2.f), (float)P.Di);
-            float wgt[8];
-            int off[8];
+    const Coords c = source_coords<PAD>(P, S);
+    const float *src = P.in + (size_t)b * P.C * Vi;
+    float *dst = P.out + (size_t)b * P.C * Vo + ((size_t)d * P.Ho + h) * P.Wo + w;
+    if (INTERP == DGTTA_INTERP_NEAREST) {
+        const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
+        const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
+        const size_t off = ok ? ((size_t)(int)rz * P.Hi + (int)ry) * P.Wi + (int)rx : 0;
+        for (int ch = 0; ch < P.C; ++ch) __stcs(dst + ch * Vo, ok ? __ldg(src + ch * Vi + off) : 0.f);
+        return;
+    }
+    Corners q = trilinear_corners(P, c);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
-                const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-                const bool ok = xx >= 0 && xx < P.Wi && yy >= 0 && yy < P.Hi && zz >= 0 && zz < P.Di;
-                const float wv = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-                wgt[k] = ok ? wv : 0.f;
-                off[k] = ok ? (zz * P.Hi + yy) * P.Wi + xx : 0;
-            }
-            for (int ch = 0; ch < P.C; ++ch) {
-                const float *s = src + ch * Vi;
-                float acc = 0.f;
+    for (int k = 0; k < 8; ++k)
+        if (q.off[k] < 0) { q.off[k] = 0; q.wgt[k] = 0.f; }
+    int ch = 0;
+    for (; ch + 4 <= P.C; ch += 4) {
+        float v[4][8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(s + off[k]), wgt[k], acc);
-                __stcs(dst + ch * Vo, acc);
-            }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = __ldg(src + (size_t)(ch + u) * Vi + q.off[k]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(v[u][k], q.wgt[k], acc);
+            __stcs(dst + (size_t)(ch + u) * Vo, acc);
         }
+    }
+    for (; ch < P.C; ++ch) {
+        const float *sp = src + (size_t)ch * Vi;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(sp + q.off[k]), q.wgt[k], acc);
+        __stcs(dst + (size_t)ch * Vo, acc);
     }
 }
 
@@ -109,45 +156,41 @@ template <int PAD>
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const __grid_constant__ SampleParams P)
 {
     // here P.in = grad_out [B,C,Do,Ho,Wo], P.out = grad_in [B,C,Di,Hi,Wi]
+    __shared__ BlockCoords S;
+    const int ntw = (P.Wo + SBX - 1) / SBX;
+    const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
+    const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
+    block_setup(P, S, b, w0, h0, d);
+    const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
+    if (w >= P.Wo || h >= P.Ho) return;
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
-    const int b = blockIdx.y;
-    __shared__ float th[12];
-    if (threadIdx.x < 12) th[threadIdx.x] = P.theta[b * 12 + threadIdx.x];
-    __syncthreads();
-    for (size_t p = (size_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x; p < Vo; p += (size_t)gridDim.x * SAMPLE_THREADS) {
-        const int w = (int)(p % P.Wo);
-        const int h = (int)((p / P.Wo) % P.Ho);
-        const int d = (int)(p / ((size_t)P.Wo * P.Ho));
-        const Coords c = source_coords<PAD>(P, th, d, h, w);
-        const float fx = floorf(c.ix), fy = floorf(c.iy), fz = floorf(c.iz);
-        const float tx = c.ix - fx, ty = c.iy - fy, tz = c.iz - fz;
-        const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)P.Wi), y0 = (int)fminf(fmaxf(fy, -2.f), (float)P.Hi),
-                  z0 = (int)fminf(fmaxf(fz, -2.f), (float)P.Di);
-        float wgt[8];
-        int off[8];
+    const Coords c = source_coords<PAD>(P, S);
+    const Corners q = trilinear_corners(P, c);
+    const float *go = P.in + (size_t)b * P.C * Vo + ((size_t)d * P.Ho + h) * P.Wo + w;
+    float *gi = P.out + (size_t)b * P.C * Vi;
+    int ch = 0;
+    for (; ch + 4 <= P.C; ch += 4) {
+        float g[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
-            const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-            const bool ok = xx >= 0 && xx < P.Wi && yy >= 0 && yy < P.Hi && zz >= 0 && zz < P.Di;
-            wgt[k] = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-            off[k] = ok ? (zz * P.Hi + yy) * P.Wi + xx : -1;
-        }
-        const float *go = P.in + (size_t)b * P.C * Vo + p;
-        float *gi = P.out + (size_t)b * P.C * Vi;
-        for (int ch = 0; ch < P.C; ++ch) {
-            const float g = __ldg(go + ch * Vo);
+        for (int u = 0; u < 4; ++u) g[u] = __ldg(go + (size_t)(ch + u) * Vo);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (off[k] >= 0) atomicAdd(gi + ch * Vi + off[k], g * wgt[k]);
-        }
+                if (q.off[k] >= 0) atomicAdd(gi + (size_t)(ch + u) * Vi + q.off[k], g[u] * q.wgt[k]);
+    }
+    for (; ch < P.C; ++ch) {
+        const float g = __ldg(go + (size_t)ch * Vo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (q.off[k] >= 0) atomicAdd(gi + (size_t)ch * Vi + q.off[k], g * q.wgt[k]);
     }
 }
 
 static int sample_check(const void *a, const void *t, const void *o, int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo)
 {
     if (!a || !t || !o) { set_error("dgtta_affine_sample: null pointer"); return DGTTA_ENULL; }
-    if (B <= 0 || C <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || B > 65535) {
+    if (B <= 0 || C <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || B > 65535 || Do > 65535) {
         set_error("dgtta_affine_sample: bad shape");
         return DGTTA_EINVAL;
     }
@@ -158,12 +201,9 @@ static int sample_check(const void *a, const void *t, const void *o, int B, int 
     return 0;
 }
 
-static dim3 sample_grid(size_t Vo, int B)
+static dim3 sample_grid(int B, int Do, int Ho, int Wo)
 {
-    size_t gx = (Vo + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
-    const size_t cap = (size_t)sm_count() * 16;  // grid-stride beyond 16 CTAs per SM
-    if (gx > cap) gx = cap;
-    return dim3((unsigned)gx, (unsigned)B, 1);
+    return dim3((unsigned)(((Wo + SBX - 1) / SBX) * ((Ho + SBY - 1) / SBY)), (unsigned)Do, (unsigned)B);
 }
 
 }  // namespace dgtta
@@ -183,13 +223,14 @@ extern "C" int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_d
     }
     cudaStream_t stream = (cudaStream_t)stream_;
     SampleParams P{in_dev, theta_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
-    const dim3 grid = sample_grid((size_t)Do * Ho * Wo, B);
+    const dim3 grid = sample_grid(B, Do, Ho, Wo);
+    const dim3 block(SBX, SBY, 1);
     if (interp == DGTTA_INTERP_TRILINEAR) {
-        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
-        else affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS><<<grid, block, 0, stream>>>(P);
+        else affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER><<<grid, block, 0, stream>>>(P);
     } else {
-        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
-        else affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+        if (padding == DGTTA_PAD_ZEROS) affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_ZEROS><<<grid, block, 0, stream>>>(P);
+        else affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_BORDER><<<grid, block, 0, stream>>>(P);
     }
     return check_launch("affine_sample_fwd_kernel");
 }
@@ -205,8 +246,9 @@ extern "C" int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const fl
     cudaError_t e = cudaMemsetAsync(grad_in_dev, 0, (size_t)B * C * Di * Hi * Wi * sizeof(float), stream);
     if (e != cudaSuccess) { set_error("dgtta_affine_sample_bwd_input: memset: %s", cudaGetErrorString(e)); return (int)e; }
     SampleParams P{grad_out_dev, theta_dev, grad_in_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
-    const dim3 grid = sample_grid((size_t)Do * Ho * Wo, B);
-    if (padding == DGTTA_PAD_ZEROS) affine_sample_bwd_kernel<DGTTA_PAD_ZEROS><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
-    else affine_sample_bwd_kernel<DGTTA_PAD_BORDER><<<grid, SAMPLE_THREADS, 0, stream>>>(P);
+    const dim3 grid = sample_grid(B, Do, Ho, Wo);
+    const dim3 block(SBX, SBY, 1);
+    if (padding == DGTTA_PAD_ZEROS) affine_sample_bwd_kernel<DGTTA_PAD_ZEROS><<<grid, block, 0, stream>>>(P);
+    else affine_sample_bwd_kernel<DGTTA_PAD_BORDER><<<grid, block, 0, stream>>>(P);
     return check_launch("affine_sample_bwd_kernel");
 }

@@ -25,8 +25,9 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f
 
 constexpr int TH = 32, TW = 32, SW = 4;          // patch, outputs per thread along W
 constexpr int NTHR = TH * (TW / SW);             // 256
-constexpr int PH = TH + 2, PWD = 40;             // staged plane: 34 rows, row pitch 40 words (cols -1..34 at +3 .. +38)
-constexpr int COL0 = 3;                          // smem column of w = w0-1; w0 sits at column 4 (16-byte aligned strips)
+constexpr int PH = TH + 2, PWD = 38;             // staged plane: 34 rows; pitch 38 words: rows alternate between banks
+                                                 // {0,1 mod 4} and {2,3 mod 4} -> conflict-free LDS.64 per half-warp
+constexpr int COL0 = 2;                          // smem column of w = w0-1 (even: every thread's 6-word window starts 8-byte aligned)
 constexpr int MAXPW = 3;                         // pointwise layers in a prologue / epilogue chain
 
 struct Pointwise {       // y_o = act(sum_i w[o][i] x_i + shift[o]); channels padded to 2 with zero weights
@@ -39,8 +40,7 @@ struct SegParams {
     const float *in;     // [rc, D, H, W] of this sample
     float *out;          // [oc, D, H, W] of this sample
     const float *x0;     // last segment: original input of this sample [1, D, H, W]
-    double *partials;    // last segment: [GIN_RED_SLOTS][2] of this sample
-    float alpha;         // unused (alpha is read from alpha_ptr: it lives on the device)
+    double *partials;    // last segment: [RED_SLOTS][2] of this sample
     const float *alpha_ptr;
     int D, H, W;
     int nTH, nTW, nCD, chunkD;
@@ -63,12 +63,19 @@ __device__ __forceinline__ void apply_pointwise(const Pointwise &L, float &c0, f
     c0 = y0; c1 = y1;
 }
 
-// Order of the reference's conv accumulation is unspecified (cuDNN / mkldnn); here: cin, kd, kh, kw ascending per
-// output plane up to the scatter order kd = 2,1,0 over successive input planes.
-template <int CIN, int COUT>
+__device__ __forceinline__ u64 lds64(const float *p) { return *reinterpret_cast<const u64 *>(p); }
+
+// Order of the reference's conv accumulation is unspecified (cuDNN / mkldnn); here: cin, kh, kw ascending per input
+// plane, planes scattered in the order kd = 2,1,0.
+// NEPI / LAST are compile-time so that the per-output epilogue carries no runtime guards.
+template <int CIN, int COUT, int NEPI, bool LAST>
 __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constant__ SegParams P)
 {
-    __shared__ __align__(16) float tile[2][CIN][PH * PWD];
+    // Every staged plane is kept twice: tileA as is, tileB shifted left by one word.  The five two-output operand
+    // pairs of a 3-tap window (x0x1, x1x2, x2x3, x3x4, x4x5) are then all 8-byte-aligned LDS.64 loads — no register
+    // shuffling to build the odd pairs.
+    __shared__ __align__(16) float tileA[2][CIN][PH * PWD];
+    __shared__ __align__(16) float tileB[2][CIN][PH * PWD];
     __shared__ double red[2][NTHR / 32];
     const int tid = threadIdx.x;
     const int D = P.D, H = P.H, W = P.W;
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
             }
         }
     };
-    auto commit = [&](int buf) {   // registers -> tile[buf], applying the prologue layers inside the volume only
+    auto commit = [&](int buf) {   // registers -> tiles, applying the prologue layers inside the volume only
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             if (cs[k] < 0) continue;
@@ -127,8 +134,9 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
                 for (int l = 0; l < MAXPW; ++l)
                     if (l < P.n_pro) apply_pointwise(P.pro[l], c0, c1);
             }
-            tile[buf][0][cs[k]] = c0;
-            if (CIN > 1) tile[buf][CIN - 1][cs[k]] = c1;
+            tileA[buf][0][cs[k]] = c0;
+            tileB[buf][0][cs[k] - 1] = c0;
+            if (CIN > 1) { tileA[buf][CIN - 1][cs[k]] = c1; tileB[buf][CIN - 1][cs[k] - 1] = c1; }
         }
     };
 
@@ -139,12 +147,13 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
         for (int o = 0; o < COUT; ++o) acc[s][o][0] = acc[s][o][1] = 0ull;
     double s_in = 0.0, s_mix = 0.0;
     float alpha = 0.f;
-    if (P.last) alpha = __ldg(P.alpha_ptr);
+    if (LAST) alpha = __ldg(P.alpha_ptr);
 
     // input planes p = d0-1 .. d1 ; plane p completes output plane p-1
     const int p_begin = d0 - 1, p_end = d1 + 1;
     if (p_begin >= 0) { fetch(p_begin); commit(0); }
     __syncthreads();
+    const int woff = ty * PWD + COL0 + SW * tx;   // row ty-1+kh (tile row ty+kh), column of w-1: even
     for (int pb = p_begin; pb < p_end; pb += 3) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
@@ -156,18 +165,14 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
             // slots: output plane q uses slot (q - p_begin + 3) % 3; with p = p_begin + 3m + u:
             //   q = p+1 -> slot (u+1)%3 (tap kd=0) , q = p -> slot u (kd=1) , q = p-1 -> slot (u+2)%3 (kd=2)
             if (p >= 0 && p < D) {
-                const float *tb = &tile[buf][0][0] + ty * PWD + COL0 + 1 + SW * tx - 1;   // row ty(-1+kh), col of w-1
 #pragma unroll
                 for (int ic = 0; ic < CIN; ++ic) {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
-                        const float *row = tb + ic * (PH * PWD) + kh * PWD;   // 6 words: w-1 .. w+4
-                        // columns: row[0] = w-1 sits at smem col COL0 + 4*tx (== 3 mod 4): load as 1 + 4 + 1
-                        const float xm = row[0];
-                        const float4 xq = *reinterpret_cast<const float4 *>(row + 1);
-                        const float xp = row[5];
-                        const u64 P01 = pk(xm, xq.x), P12 = pk(xq.x, xq.y), P23 = pk(xq.y, xq.z), P34 = pk(xq.z, xq.w),
-                                  P45 = pk(xq.w, xp);
+                        const float *ra = &tileA[buf][ic][woff + kh * PWD];
+                        const float *rb = &tileB[buf][ic][woff + kh * PWD];
+                        const u64 P01 = lds64(ra), P23 = lds64(ra + 2), P45 = lds64(ra + 4);
+                        const u64 P12 = lds64(rb), P34 = lds64(rb + 2);
 #pragma unroll
                         for (int kd = 0; kd < 3; ++kd) {
                             const int slot = (kd == 0) ? (u + 1) % 3 : (kd == 1 ? u : (u + 2) % 3);
@@ -200,19 +205,25 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
                 }
                 const size_t off = (size_t)q * HW + (size_t)oh * W + ow;
                 float xin[SW];
-                if (P.last) {
+                if (LAST) {
+                    if (vec_ok) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(P.x0 + off));
+                        xin[0] = xv.x; xin[1] = xv.y; xin[2] = xv.z; xin[3] = xv.w;
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < SW; ++k) xin[k] = ok[k] ? __ldg(P.x0 + off + k) : 0.f;
+                        for (int k = 0; k < SW; ++k) xin[k] = ok[k] ? __ldg(P.x0 + off + k) : 0.f;
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < SW; ++k) {
                     float c0 = y[0][k] + P.cshift[0], c1 = y[1][k] + P.cshift[1];        // gin.py:111
-                    if (P.conv_act) { c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f; }   // gin.py:112-113
+                    if (!(LAST && NEPI == 0)) {   // the conv layer itself is the stack's last layer only then: no activation
+                        c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f;   // gin.py:112-113
+                    }
                     if (COUT == 1) c1 = 0.f;
 #pragma unroll
-                    for (int l = 0; l < MAXPW; ++l)
-                        if (l < P.n_epi) apply_pointwise(P.epi[l], c0, c1);
-                    if (P.last) {
+                    for (int l = 0; l < NEPI; ++l) apply_pointwise(P.epi[l], c0, c1);
+                    if (LAST) {
                         c0 = __fadd_rn(__fmul_rn(alpha, c0), __fmul_rn(1.0f - alpha, xin[k]));   // gin.py:197
                         if (ok[k]) { s_in += (double)xin[k] * xin[k]; s_mix += (double)c0 * c0; }
                     }
@@ -220,13 +231,13 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
                 }
                 if (vec_ok) {
                     *reinterpret_cast<float4 *>(P.out + off) = make_float4(y[0][0], y[0][1], y[0][2], y[0][3]);
-                    if (P.oc > 1) *reinterpret_cast<float4 *>(P.out + V + off) = make_float4(y[1][0], y[1][1], y[1][2], y[1][3]);
+                    if (!LAST && P.oc > 1) *reinterpret_cast<float4 *>(P.out + V + off) = make_float4(y[1][0], y[1][1], y[1][2], y[1][3]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < SW; ++k)
                         if (ok[k]) {
                             P.out[off + k] = y[0][k];
-                            if (P.oc > 1) P.out[V + off + k] = y[1][k];
+                            if (!LAST && P.oc > 1) P.out[V + off + k] = y[1][k];
                         }
                 }
             }
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
             __syncthreads();   // next plane staged by everyone; this plane's buffer free for re-staging
         }
     }
-    if (P.last) {
+    if (LAST) {
         s_in = warp_sum(s_in); s_mix = warp_sum(s_mix);
         if ((tid & 31) == 0) { red[0][tid >> 5] = s_in; red[1][tid >> 5] = s_mix; }
         __syncthreads();
@@ -248,6 +259,22 @@ __global__ void __launch_bounds__(NTHR) gin_conv_seg_kernel(const __grid_constan
             atomicAdd(&P.partials[2 * slot], a);
             atomicAdd(&P.partials[2 * slot + 1], m);
         }
+    }
+}
+
+template <int CIN, int COUT>
+static void launch_conv(const SegParams &P, unsigned grid, cudaStream_t stream)
+{
+    // the reachable (NEPI, LAST) combinations: the epilogue holds the 1x1x1 layers up to the next 3x3x3 layer or the end
+    const int code = P.n_epi * 2 + (P.last ? 1 : 0);
+    switch (code) {
+        case 0: gin_conv_seg_kernel<CIN, COUT, 0, false><<<grid, NTHR, 0, stream>>>(P); break;
+        case 1: gin_conv_seg_kernel<CIN, COUT, 0, true><<<grid, NTHR, 0, stream>>>(P); break;
+        case 2: gin_conv_seg_kernel<CIN, COUT, 1, false><<<grid, NTHR, 0, stream>>>(P); break;
+        case 3: gin_conv_seg_kernel<CIN, COUT, 1, true><<<grid, NTHR, 0, stream>>>(P); break;
+        case 4: gin_conv_seg_kernel<CIN, COUT, 2, false><<<grid, NTHR, 0, stream>>>(P); break;
+        case 5: gin_conv_seg_kernel<CIN, COUT, 2, true><<<grid, NTHR, 0, stream>>>(P); break;
+        default: gin_conv_seg_kernel<CIN, COUT, 3, true><<<grid, NTHR, 0, stream>>>(P); break;
     }
 }
 
@@ -321,7 +348,6 @@ int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_hos
     if (ncd < 1) ncd = 1;
     P.chunkD = (D + ncd - 1) / ncd;
     P.nCD = (D + P.chunkD - 1) / P.chunkD;
-    P.alpha = 0.f;
 
     for (int b = 0; b < B; ++b) {
         P.alpha_ptr = alphas_dev + b;
@@ -369,9 +395,9 @@ int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_hos
             float *dst = last_seg ? out_dev + (size_t)b * V : ((s & 1) ? buf1 : buf0) + (size_t)b * 2 * V;
             P.out = dst;
             const unsigned grid = (unsigned)(base * P.nCD);
-            if (ci == 1 && co == 2) gin_conv_seg_kernel<1, 2><<<grid, NTHR, 0, stream>>>(P);
-            else if (ci == 2 && co == 2) gin_conv_seg_kernel<2, 2><<<grid, NTHR, 0, stream>>>(P);
-            else gin_conv_seg_kernel<2, 1><<<grid, NTHR, 0, stream>>>(P);
+            if (ci == 1 && co == 2) launch_conv<1, 2>(P, grid, stream);
+            else if (ci == 2 && co == 2) launch_conv<2, 2>(P, grid, stream);
+            else launch_conv<2, 1>(P, grid, stream);
             int rc = check_launch("gin_conv_seg_kernel");
             if (rc) return rc;
             cur = dst;

@@ -30,7 +30,12 @@ def get_rand_affine(batch_size, strength=0.05, flip=False):
 def _theta_on(device, theta, B):
     if tuple(theta.shape) != (B, 3, 4):
         raise ValueError(f"theta must have shape [{B},3,4], got {tuple(theta.shape)}")
-    return theta.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    theta = theta.to(dtype=torch.float32)
+    if not theta.is_cuda:
+        # 96 bytes per sample: stage through pinned memory so the upload is a truly asynchronous copy
+        # (a pageable-source .to(device) synchronises the host with the stream)
+        theta = theta.contiguous().pin_memory()
+    return theta.to(device=device, non_blocking=True).contiguous()
 
 
 class _AffineSample(torch.autograd.Function):
