@@ -18,38 +18,58 @@
 // Global clamp (mind.py:158-160): pass 1 assumes it inactive and records {sum v, min positive v, max v}
 // per (CTA, batch).  mind_fast_finalize reduces them to mean_all(v) and lists the (CTA, batch) units whose
 // range leaves [0.001*mean, 1000*mean]; pass 2 recomputes exactly those 4-plane units with the clamp.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "mind_internal.cuh"
 
 namespace dgtta {
 
 namespace fast {
 
+// internal noise mode: DGTTA_NOISE_TENSOR whose field is staged by TMA (cp.async.bulk.tensor) straight into the
+// E^2 planes of shared memory, one 40 x 20 x 12-channel box per plane, and squared in place by S1.  TMA wants the
+// innermost start coordinate 16-byte aligned (measured: a start of w0-2 floats raises an illegal-instruction trap,
+// tools/microbench/tma_probe.cu), so this mode widens the halo tile to the aligned columns [w0-4, w0+36).  Needs
+// W % 4 == 0, a 16-byte aligned tensor and delta <= 2 (shared memory); everything else keeps the LDG path.
+constexpr int NOISE_TMA = 3;
+
 constexpr int R = 2, NT = 5, PB = 4, NWIN = NT - 1;   // PB == NWIN keeps the D-window slots compile-time
 constexpr int EH = MIND_TH + 2 * R;   // 20 halo rows
-constexpr int EW = MIND_TW + 2 * R;   // 36 halo columns
-constexpr int TWD = 44;               // tile row pitch: 4 pad + 36 + 4 pad words (conflict-free LDS.128 across rows)
-constexpr int WSP = EW;                    // ws row pitch 36: rows 4 banks apart -> conflict-free LDS/STS.128 across rows
-constexpr int WS_CH = EH * WSP + 20;       // 740 words = 185 16-byte chunks == 1 (mod 8): consecutive S2 tasks (9 strips per channel) stay conflict-free
-constexpr int WS_PLANE = 12 * WS_CH;
-constexpr int NQUAD = EW / 4;              // 9 position quads per halo row
-constexpr int S1_TASKS = PB * EH * NQUAD;  // 720
-constexpr int S2_TASKS = PB * 12 * NQUAD;  // 432 column-strip tasks: a single round
 constexpr int C_WARPS = MIND_TH;           // 16 warps own the patch rows in stage C
 constexpr int NTHREADS = MIND_THREADS;     // 512
-static_assert(S2_TASKS <= NTHREADS, "S2 must fit one round");
 
-template <int DELTA>
+// Halo-tile geometry per noise mode.  LDG modes: 36 halo columns [w0-2, w0+34), ws channel pitch 740 words = 185
+// 16-byte chunks == 1 (mod 8) so that consecutive S2 tasks (9 strips per channel) stay conflict-free.  TMA mode: 40
+// columns [w0-4, w0+36) (the outer two on each side are computed but never read), dense box layout (800 words).
+template <int NOISE> struct Mode {
+    static constexpr bool TMA = NOISE == NOISE_TMA;
+    static constexpr int CO = TMA ? 4 : R;             // halo column 0 is w0 - CO
+    static constexpr int EW = MIND_TW + 2 * CO;        // halo columns: 40 / 36
+    static constexpr int NQUAD = EW / 4;               // position quads per halo row: 10 / 9
+    static constexpr int TWD = EW + 8;                 // image tile row pitch: 4 pad + EW + 4 pad words
+    static constexpr int WSP = EW;                     // ws row pitch
+    static constexpr int WS_CH = TMA ? EH * WSP : EH * WSP + 20;
+    static constexpr int WS_PLANE = 12 * WS_CH;
+    static constexpr int NSW = TMA ? PB + 1 : PB;      // ws plane ring: one spare plane lets noise of the next batch fly under C
+    static constexpr int S1_TASKS = PB * EH * NQUAD;   // 800 / 720
+    static constexpr int S2_TASKS = PB * 12 * NQUAD;   // 480 / 432 column-strip tasks: a single round
+    static_assert(S2_TASKS <= NTHREADS, "S2 must fit one round");
+};
+
+template <int DELTA, int NOISE>
 struct Geom {
+    using M = Mode<NOISE>;
     static constexpr int TR = EH + 2 * DELTA;        // tile rows
-    static constexpr int TCOLS = EW + 2 * DELTA;     // loaded tile columns
+    static constexpr int TCOLS = M::EW + 2 * DELTA;  // loaded tile columns
     static constexpr int NSLOT = PB + 2 * DELTA;     // ring of image planes
-    static constexpr int TILE = TR * TWD;
+    static constexpr int TILE = TR * M::TWD;
     static constexpr int CELLS = TR * TCOLS;
     static constexpr int NCELL = (CELLS + NTHREADS - 1) / NTHREADS;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(PB * WS_PLANE + NSLOT * TILE);
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(M::NSW * M::WS_PLANE + NSLOT * TILE);
 };
 
 struct Params {
+    alignas(64) CUtensorMap noise_map;   // NOISE_TMA: 4-D view (W, H, D, B*12) of the noise tensor, box 40 x 20 x 1 x 12
     const float *img;
     float *out;
     const float *noise;
@@ -59,6 +79,7 @@ struct Params {
     const float *fix_lohi;
     int B, D, H, W;
     int nTH, nTW, nCD, chunkD, nbatch;
+    int stagger;          // cycles: CTA i starts (i mod 4) * stagger late so that the SMs' store phases do not coincide
     float rw;
     float taps[NT];
 };
@@ -70,6 +91,53 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- mbarrier / TMA (sm_90+ PTX; SASS SYNCS.* / UTMALDG)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(float *dst_smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// Hides a value's provenance from the optimiser: per-thread constants derived from opaque(tid) inside the batch loop
+// are recomputed each batch (a dozen integer instructions) instead of living in registers across stage C, which
+// runs at the 128-register cap.
+__device__ __forceinline__ int opaque(int x)
+{
+    asm volatile("" : "+r"(x));
+    return x;
+}
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -109,12 +177,17 @@ __device__ __forceinline__ void st4p(float *p, u64 a, u64 b)
 
 // March one CTA over output planes [d0, d1) of patch (h0, w0) of sample b.
 template <int DELTA, int NOISE, bool FIX>
-__device__ __forceinline__ void process(const Params &P, float *smem, float (*red)[C_WARPS], int b, int h0,
-                                        int w0, int d0, int d1, float lo, float hi, float4 *stats)
+__device__ __forceinline__ void process(const Params &P, float *smem, float (*red)[C_WARPS], uint64_t *full_bar,
+                                        uint64_t *empty_bar, int b, int h0, int w0, int d0, int d1, float lo, float hi,
+                                        float4 *stats)
 {
-    using G = Geom<DELTA>;
+    using G = Geom<DELTA, NOISE>;
+    using M = Mode<NOISE>;
+    constexpr bool TMA = M::TMA;
+    constexpr int CO = M::CO, NQUAD = M::NQUAD, TWD = M::TWD, WSP = M::WSP;
+    constexpr int WS_CH = M::WS_CH, WS_PLANE = M::WS_PLANE, NSW = M::NSW, S1_TASKS = M::S1_TASKS, S2_TASKS = M::S2_TASKS;
     float *ws = smem;
-    float *tiles = smem + PB * WS_PLANE;
+    float *tiles = smem + NSW * WS_PLANE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = P.D, H = P.H, W = P.W, HW = H * W;
     const float *img = P.img + (size_t)b * D * HW;
@@ -123,23 +196,20 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 #pragma unroll
     for (int t = 0; t < NT; ++t) G2[t] = pk(P.taps[t], P.taps[t]);
 
-    // ---- T: per-thread tile cells (plane-invariant)
-    int cell_s[G::NCELL], cell_g[G::NCELL];
-#pragma unroll
-    for (int k = 0; k < G::NCELL; ++k) {
-        const int i = tid + k * NTHREADS;
-        if (i < G::CELLS) {
-            const int rr = i / G::TCOLS, cc = i - rr * G::TCOLS;
-            cell_s[k] = rr * TWD + (4 - DELTA) + cc;
-            cell_g[k] = clampi(h0 - R - DELTA + rr, 0, H - 1) * W + clampi(w0 - R - DELTA + cc, 0, W - 1);
-        } else {
-            cell_s[k] = -1;
-            cell_g[k] = 0;
-        }
-    }
+    // ---- T: image tile cells of this thread (plane-invariant, recomputed per call: see opaque())
     int loaded_hi;  // highest real plane resident in the ring
     auto load_until = [&](int need_hi) {
         need_hi = min(need_hi, D - 1);
+        if (loaded_hi >= need_hi) { cp_async_commit(); return; }
+        const int t0 = opaque(tid);
+        int cell_s[G::NCELL], cell_g[G::NCELL];
+#pragma unroll
+        for (int k = 0; k < G::NCELL; ++k) {
+            const int i = t0 + k * NTHREADS;
+            const int rr = i / G::TCOLS, cc = i - rr * G::TCOLS;
+            cell_s[k] = i < G::CELLS ? rr * TWD + (4 - DELTA) + cc : -1;
+            cell_g[k] = clampi(h0 - R - DELTA + rr, 0, H - 1) * W + clampi(w0 - CO - DELTA + cc, 0, W - 1);
+        }
         for (int p = loaded_hi + 1; p <= need_hi; ++p) {
             float *dst = tiles + (p % G::NSLOT) * G::TILE;
             const float *src = img + (size_t)p * HW;
@@ -147,39 +217,29 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             for (int k = 0; k < G::NCELL; ++k)
                 if (cell_s[k] >= 0) cp_async4(dst + cell_s[k], src + cell_g[k]);
         }
-        loaded_hi = max(loaded_hi, need_hi);
+        loaded_hi = need_hi;
         cp_async_commit();
     };
 
     // halo rows / columns outside the volume replicate E^2 of the clamped position (mind.py:22)
     const int rT = max(0, R - h0), rB = min(EH - 1, H - 1 - h0 + R);
-    const int eR = W - 1 - w0 + R;               // halo column index of w = W-1
+    const int eR = W - 1 - w0 + CO;              // halo column index of w = W-1
     const bool scaled = P.in_scale != nullptr;
-    u64 SA = pk(1.f, 1.f), SC = SA;
-    if (scaled) { SA = pk(P.in_scale[2 * b], P.in_scale[2 * b]); SC = pk(P.in_scale[2 * b + 1], P.in_scale[2 * b + 1]); }
     const u64 RW = pk(P.rw, P.rw);
-    const bool noise_vec = (NOISE == DGTTA_NOISE_TENSOR) && ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.noise) & 7) == 0);
-
-    // ---- S2 bookkeeping: one (plane, channel, column quad) task per thread, exactly one round
-    const bool s2_active = tid < S2_TASKS;
-    const int s2_pc = tid / NQUAD;                   // pz * 12 + c
-    const int s2_pz = s2_pc / 12;
-    const int s2_off = s2_pz * WS_PLANE + (s2_pc - s2_pz * 12) * WS_CH + 4 * (tid - s2_pc * NQUAD);
+    const bool noise_vec = (NOISE != DGTTA_NOISE_NONE) && ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.noise) & 7) == 0);
 
     // ---- C bookkeeping: warp = patch row, lane = (4-column group wl, channel group cg)
     const bool c_active = warp < C_WARPS;
     const int wl = lane & 7, cg = lane >> 3;
-    const int c_off = (3 * cg) * WS_CH + warp * WSP + 4 * wl;
+    const int c_off = (3 * cg) * WS_CH + warp * WSP + 4 * wl;   // halo columns 4wl .. : the thread's voxels are 4wl+CO-R ..
     const int vh = h0 + warp, vw = w0 + 4 * wl;
     const bool row_ok = c_active && vh < H;
-    bool valid[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) valid[k] = row_ok && (vw + k < W);
+    auto valid = [&](int k) { return row_ok && vw + k < W; };
     // per-channel output pointers of the thread's 4-voxel run, advanced plane by plane
     // running output pointer of the thread's 4-voxel run (channel 3*cg), advanced by one plane per emit
     float *op = P.out + (((size_t)b * 12 + 3 * cg) * D + d0) * HW + (size_t)vh * W + vw;
     const size_t ch_stride = (size_t)D * HW;
-    const bool vec_store = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && ((W & 3) == 0) && valid[3];
+    const bool vec_store = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && ((W & 3) == 0) && valid(3);
     const bool stat_lane = cg == 0;
 
     u64 win[3][2][NWIN];   // the last 4 W-smoothed planes of the thread's 4 voxels x 3 channels
@@ -192,6 +252,30 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 
     const int z_begin = d0 - R, z_end = d1 + R;
     const int nb = (z_end - z_begin + PB - 1) / PB;
+
+    // ---- NOISE_TMA: marched plane g (= z_begin + g) lives in ws slot g % NSW.  One thread arms full_bar[slot] and
+    // issues the box copy; S1 waits on the barrier, adds the noise it finds at its own E^2 address and overwrites it.
+    // A slot is refilled (plane g + NSW) by the last warp that finishes reading plane g in stage C.
+    auto issue_noise = [&](int s, int z) {   // marched plane z -> slot s
+        if (z >= z_end) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads/writes of the slot before the async write
+        mbar_expect_tx(&full_bar[s], (unsigned)(WS_PLANE * sizeof(float)));
+        tma_load_4d(ws + s * WS_PLANE, &P.noise_map, &full_bar[s], w0 - CO, h0 - R, clampi(z, 0, D - 1), b * 12);
+    };
+    // slot of plane pz of the current batch = slot0 + pz (mod NSW); bit s of fill_parity = parity of the fill S1 waits for
+    int slot0 = 0;
+    unsigned fill_parity = 0;
+    auto slot_of = [&](int pz) { int sl = slot0 + pz; return TMA ? (sl >= NSW ? sl - NSW : sl) : pz; };
+    if (TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < NSW; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], C_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < NSW; ++g) issue_noise(g, z_begin + g);
+        }
+        // the first __syncthreads of the batch loop publishes the barriers before anyone waits on them
+    }
 
     // first batch: everything it needs
     loaded_hi = max(clampi(z_begin, 0, D - 1) - DELTA, 0) - 1;
@@ -217,6 +301,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             const int rem = t - pz * (EH * NQUAD);
             const int r = rem / NQUAD, q = rem - r * NQUAD;
             if (zb + pz >= z_end) continue;
+            if (TMA && (r < rT || r > rB || w0 - CO + 4 * q < 0 || w0 - CO + 4 * q >= W)) continue;   // not an owner (see below)
             const int zc = clampi(zb + pz, 0, D - 1);
             const int rc = clampi(r, rT, rB);
             const int toff = (rc + DELTA) * TWD + 4 + 4 * q;   // centre row, first position of the quad
@@ -233,11 +318,12 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             float wm[4], wp[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { wm[k] = wr[4 + k - DELTA]; wp[k] = wr[4 + k + DELTA]; }
-            if (w0 == 0 && q == 0) {
-                // columns w = -2,-1 take E of w = 0: only the W+ neighbour differs from the clamped loads
-                wp[0] = wp[2]; wp[1] = wp[2];
+            if (!TMA && w0 == 0 && q == 0) {
+                // columns w < 0 take E of w = 0: only the W+ neighbour (I at w = delta) differs from the clamped loads
+#pragma unroll
+                for (int k = 0; k < CO; ++k) wp[k] = wr[4 + CO + DELTA];
             }
-            if (4 * q + 3 > eR) {
+            if (!TMA && 4 * q + 3 > eR) {
                 // columns beyond w = W-1 take E of w = W-1: only the W- neighbour differs
                 const float wm_fix = tiles[(zc % G::NSLOT) * G::TILE + (rc + DELTA) * TWD + 4 + eR - DELTA];
 #pragma unroll
@@ -246,17 +332,52 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             nbv[NB_WM][0] = pk(wm[0], wm[1]); nbv[NB_WM][1] = pk(wm[2], wm[3]);
             nbv[NB_WP][0] = pk(wp[0], wp[1]); nbv[NB_WP][1] = pk(wp[2], wp[3]);
             if (scaled) {
+                const float sa = __ldg(P.in_scale + 2 * b), sc = __ldg(P.in_scale + 2 * b + 1);
+                const u64 SA = pk(sa, sa), SC = pk(sc, sc);
 #pragma unroll
                 for (int a = 0; a < 6; ++a)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) nbv[a][j] = fmul2(fmul2(nbv[a][j], SA), SC);
             }
-            float *wsp = ws + pz * WS_PLANE + r * WSP + 4 * q;
-            if (NOISE == DGTTA_NOISE_TENSOR) {
+            float *wsp = ws + slot_of(pz) * WS_PLANE + r * WSP + 4 * q;
+            const int gw0 = w0 - CO + 4 * q;
+            if (TMA) {
+                // The task owns its quad only if row and quad lie inside the volume (W % 4 == 0: a quad is in or out as a
+                // whole); halo positions outside replicate E^2 of the clamped position (mind.py:22) and are written by
+                // the task that owns that position, so nobody reads noise another task may already have squared.
+                const int sl = slot_of(pz);
+                mbar_wait(&full_bar[sl], (fill_parity >> sl) & 1u);   // also orders our E^2 stores after the box write
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    u64 n0, n1;
+                    ld4p(wsp + c * WS_CH, n0, n1);
+                    u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
+                    u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
+                    e0 = fadd2(e0, fmul2(RW, n0));   // product and sum rounded separately, like the reference
+                    e1 = fadd2(e1, fmul2(RW, n1));
+                    st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
+                }
+                const int nup = r == rT ? rT : 0;                                  // halo rows above the volume
+                const int ndn = r == rB ? min(R, EH - 1 - rB) : 0;                 // halo rows below that valid outputs read
+                const bool left = gw0 == 0 && q > 0, right = gw0 + 4 == W && q + 1 < NQUAD;
+                if (nup | ndn | (int)left | (int)right) {
+#pragma unroll 1
+                    for (int rr = -nup; rr <= ndn; ++rr) {
+                        if (rr == 0 && !left && !right) continue;
+                        float *d = wsp + rr * WSP;
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) {
+                            const float4 e = *reinterpret_cast<const float4 *>(wsp + c * WS_CH);
+                            if (rr) *reinterpret_cast<float4 *>(d + c * WS_CH) = e;
+                            if (left) *reinterpret_cast<float4 *>(d + c * WS_CH - 4) = make_float4(e.x, e.x, e.x, e.x);
+                            if (right) *reinterpret_cast<float4 *>(d + c * WS_CH + 4) = make_float4(e.w, e.w, e.w, e.w);
+                        }
+                    }
+                }
+            } else if (NOISE != DGTTA_NOISE_NONE) {
                 // noise of the (clamped) positions: mind.py:150-152 adds rw*N to the edge before squaring; halo
                 // positions outside the volume reuse the sample of the clamped position (they replicate E^2)
                 const float *nz = P.noise + ((size_t)b * 12 * D + zc) * HW + (size_t)clampi(h0 - R + r, 0, H - 1) * W;
-                const int gw0 = w0 - R + 4 * q;
                 const bool interior = gw0 >= 0 && gw0 + 3 < W && noise_vec;   // uniform per task, 8-byte aligned pairs
                 int ngw[4];
 #pragma unroll
@@ -298,8 +419,12 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         __syncthreads();
 
         // ================= S2: H smoothing of a 4-column strip, in place, sliding 5-row register window
-        if (s2_active && zb + s2_pz < z_end) {
-            float *col = ws + s2_off;
+        // one (plane, channel, column quad) task per thread, exactly one round
+        const int s2_t = opaque(tid);
+        const int s2_pc = s2_t / NQUAD;                  // pz * 12 + c
+        const int s2_pz = s2_pc / 12;
+        if (s2_t < S2_TASKS && zb + s2_pz < z_end) {
+            float *col = ws + slot_of(s2_pz) * WS_PLANE + (s2_pc - s2_pz * 12) * WS_CH + 4 * (s2_t - s2_pc * NQUAD);
             u64 acc[NT][2];   // partial sums of the 5 output rows that input row r contributes to
 #pragma unroll
             for (int r = 0; r < EH; ++r) {
@@ -322,7 +447,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         // prefetch the image planes of the next batch while C runs
         if (n + 1 < nb) {
             load_until(clampi(zb + 2 * PB - 1, 0, D - 1) + DELTA);
-            if (NOISE == DGTTA_NOISE_TENSOR) {
+            if (NOISE == DGTTA_NOISE_TENSOR) {   // (NOISE_TMA: the boxes are already in flight)
                 // pull the next batch's noise rows (144 B each) into L2 so that S1's loads do not pay DRAM latency
                 for (int i = tid; i < 12 * PB * EH; i += NTHREADS) {
                     const int c = i / (PB * EH), rem = i - c * (PB * EH);
@@ -347,14 +472,21 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                     // No branch around a plane: planes past z_end (tail of the last batch) read stale but finite ws
                     // data and are never emitted, so the four plane steps form one straight-line block that the
                     // scheduler can overlap (loads / W pass of plane p+1 under the shuffle+MUFU chain of plane p).
-                    const float *wsp = ws + ph * WS_PLANE + c_off;
+                    const float *wsp = ws + slot_of(ph) * WS_PLANE + c_off;
                     const bool emit = (z - R) >= d0 && z < z_end;   // uniform
                     u64 m[3][2];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        float v[8];
-                        ld4(wsp + a * WS_CH, &v[0]);
-                        ld4(wsp + a * WS_CH + 4, &v[4]);
+                        float v[8];   // the 5-tap window of voxel k starts at v[k] = halo column 4wl + k + CO - R
+                        if (TMA) {
+                            const float2 f0 = *reinterpret_cast<const float2 *>(wsp + a * WS_CH + 2);
+                            const float2 f1 = *reinterpret_cast<const float2 *>(wsp + a * WS_CH + 8);
+                            v[0] = f0.x; v[1] = f0.y; v[6] = f1.x; v[7] = f1.y;
+                            ld4(wsp + a * WS_CH + 4, &v[2]);
+                        } else {
+                            ld4(wsp + a * WS_CH, &v[0]);
+                            ld4(wsp + a * WS_CH + 4, &v[4]);
+                        }
                         // o_k = g2 v[k+2] + g1 (v[k+1] + v[k+3]) + g0 (v[k] + v[k+4]),  k = 0..3, two lanes at a time
                         const u64 s0a = fadd2(pk(v[0], v[1]), pk(v[4], v[5]));
                         const u64 s0b = fadd2(pk(v[2], v[3]), pk(v[6], v[7]));
@@ -404,7 +536,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                                 v = fminf(fmaxf(v, lo), hi);                               // mind.py:158-160
                                 sc2[e] = -1.4426950408889634f * rcp_approx(v);
                             } else {
-                                const bool cnt = stat_lane && emit && valid[2 * j + e];
+                                const bool cnt = stat_lane && emit && valid(2 * j + e);
                                 st_sum += cnt ? v : 0.f;
                                 st_max = fmaxf(st_max, cnt ? v : 0.f);
                                 st_min = fminf(st_min, (cnt && v > 0.f) ? v : __int_as_float(0x7f800000));
@@ -433,15 +565,37 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                         for (int a = 0; a < 3; ++a)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                if (valid[k]) __stcs(op + a * ch_stride + k, o[a][k]);
+                                if (valid(k)) __stcs(op + a * ch_stride + k, o[a][k]);
                     }
                     op += emit ? HW : 0;
+                    if (TMA) {
+                        // this warp is done with the plane: arrive on the slot's empty barrier.  Thread 0 (lowest issue
+                        // priority, so usually the last warp anyway) refills the slot with plane z + NSW one plane later,
+                        // when the other 15 warps have normally arrived already.
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[slot_of(ph)]);
+                        if (ph > 0 && tid == 0) {
+                            const int sl = slot_of(ph - 1);
+                            mbar_wait(&empty_bar[sl], (fill_parity >> sl) & 1u);
+                            issue_noise(sl, z - 1 + NSW);
+                        }
+                    }
                 }
+            }
+            if (TMA && tid == 0) {
+                const int sl = slot_of(PB - 1);
+                mbar_wait(&empty_bar[sl], (fill_parity >> sl) & 1u);
+                issue_noise(sl, zb + PB - 1 + NSW);
             }
             if (!FIX) {
                 st_sum = warp_sum(st_sum); st_min = warp_min(st_min); st_max = warp_max(st_max);
                 if (lane == 0) { red[0][warp] = st_sum; red[1][warp] = st_min; red[2][warp] = st_max; }
             }
+        }
+        if (TMA) {
+            // the batch consumed one fill of each of its PB slots; the next batch starts PB slots further round the ring
+            fill_parity ^= ((1u << NSW) - 1u) ^ (1u << slot_of(PB));
+            slot0 = slot_of(PB);
         }
     }
     if (!FIX) {
@@ -454,6 +608,14 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             if (lane == 0) stats[nb - 1] = make_float4(s, mnv, mxv, 0.f);
             // batches this (shorter) chunk never ran: neutral entries
             for (int i = nb + lane; i < P.nbatch; i += 32) stats[i] = make_float4(0.f, __int_as_float(0x7f800000), 0.f, 0.f);
+        }
+    }
+    if (TMA && FIX) {
+        // the persistent fix kernel re-arms the barriers for its next unit; every issued box has been consumed by S1
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < NSW; ++s) { mbar_inval(&full_bar[s]); mbar_inval(&empty_bar[s]); }
         }
     }
 }
@@ -472,19 +634,28 @@ __device__ __forceinline__ void decode_cta(const Params &P, int cta, int &b, int
 template <int DELTA, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, 1) mind_fast_kernel(const __grid_constant__ Params P)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ float red[3][C_WARPS];
+    __shared__ uint64_t full_bar[PB + 1];
+    __shared__ uint64_t empty_bar[PB + 1];
     int b, h0, w0, d0, d1;
     decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
-    process<DELTA, NOISE, false>(P, smem, red, b, h0, w0, d0, d1, 0.f, 0.f, P.stats + (size_t)blockIdx.x * P.nbatch);
+    if (P.stagger > 0) {
+        const long long t0 = clock64(), wait = (long long)(blockIdx.x & 3) * P.stagger;
+        while (clock64() - t0 < wait) {}
+    }
+    process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, b, h0, w0, d0, d1, 0.f, 0.f,
+                                 P.stats + (size_t)blockIdx.x * P.nbatch);
 }
 
 // pass 2: persistent CTAs walk the list of (CTA, batch) units whose clamp is active
 template <int DELTA, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, 1) mind_fast_fix_kernel(const __grid_constant__ Params P)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ float red[3][C_WARPS];
+    __shared__ uint64_t full_bar[PB + 1];
+    __shared__ uint64_t empty_bar[PB + 1];
     const int count = P.fix_hdr[0];
     const float lo = P.fix_lohi[0], hi = P.fix_lohi[1];
     for (int u = blockIdx.x; u < count; u += gridDim.x) {
@@ -494,7 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mind_fast_fix_kernel(const __grid
         decode_cta(P, cta, b, h0, w0, d0, d1);
         // batch n of pass 1 emitted planes d0 + PB*n - 2R .. + PB-1 (clipped to the chunk)
         const int lo_d = max(d0, d0 + n * PB - 2 * R), hi_d = min(d1 - 1, d0 + n * PB - 2 * R + PB - 1);
-        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
+        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, full_bar, empty_bar, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
         __syncthreads();
     }
 }
@@ -567,7 +738,7 @@ static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 template <int DELTA, int NOISE>
 static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStream_t stream)
 {
-    using G = Geom<DELTA>;
+    using G = Geom<DELTA, NOISE>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(mind_fast_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
@@ -592,10 +763,50 @@ static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStrea
     return check_launch("mind_fast_fix_kernel");
 }
 
-template <int DELTA>
-static int launch_noise(const Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
 {
-    if (noise_mode == DGTTA_NOISE_TENSOR) return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 4-D view (W, H, D, B*12) of the [B,12,D,H,W] noise tensor; box = one halo tile of all 12 channels of one plane
+static bool make_noise_map(Params &P)
+{
+    if ((P.W & 3) || (reinterpret_cast<uintptr_t>(P.noise) & 15)) return false;
+    if (getenv("DGTTA_MIND_NO_TMA")) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.D, (cuuint64_t)P.B * 12};
+    const cuuint64_t strides[3] = {(cuuint64_t)P.W * 4, (cuuint64_t)P.H * P.W * 4, (cuuint64_t)P.D * P.H * P.W * 4};
+    const cuuint32_t box[4] = {Mode<NOISE_TMA>::EW, EH, 1, 12};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(&P.noise_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(P.noise), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int DELTA>
+static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
+{
+    if (noise_mode == DGTTA_NOISE_TENSOR) {
+        if (DELTA <= 2 && make_noise_map(P)) return launch<DELTA <= 2 ? DELTA : 1, NOISE_TMA>(P, plan, workspace, stream);
+        return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
+    }
     return launch<DELTA, DGTTA_NOISE_NONE>(P, plan, workspace, stream);
 }
 
@@ -627,11 +838,13 @@ int mind_fast_launch(const MindArgs &a, cudaStream_t stream)
         return DGTTA_EWORKSPACE;
     }
     fast::Params P;
+    memset(&P.noise_map, 0, sizeof(P.noise_map));
     P.img = a.img; P.out = a.out; P.noise = a.noise; P.in_scale = a.in_scale;
     P.stats = nullptr; P.fix_hdr = nullptr; P.fix_lohi = nullptr;
     P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W;
     P.nTH = plan.nTH; P.nTW = plan.nTW; P.nCD = plan.nCD; P.chunkD = plan.chunkD; P.nbatch = plan.nbatch;
     P.rw = a.rw;
+    { const char *e = getenv("DGTTA_MIND_STAGGER"); P.stagger = e ? atoi(e) : 0; }
     for (int i = 0; i < fast::NT; ++i) P.taps[i] = a.taps[i];
     switch (a.delta) {
         case 1: return fast::launch_noise<1>(P, plan, a.workspace, a.noise_mode, stream);

@@ -117,3 +117,37 @@ def test_full_size_properties(shape, delta):
     # oracle on the whole volume is cheap in C (seconds)
     ref = cform.mind_ssc(x.cpu().numpy(), delta=delta, noise=None)
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("shape,delta", [((1, 1, 64, 64, 64), 1), ((2, 1, 40, 36, 72), 2), ((1, 1, 21, 12, 8), 1),
+                                         ((1, 1, 50, 100, 132), 3), ((2, 1, 192, 192, 192), 1)])
+def test_tma_staged_noise_is_bitwise_the_ldg_path(shape, delta, monkeypatch):
+    """W % 4 == 0 takes the TMA-staged noise path (box copies into the E^2 planes); DGTTA_MIND_NO_TMA forces the
+    LDG path.  Same arithmetic -> bit-identical descriptors; the small cases are also checked against the oracle."""
+    from dg_tta_b200 import MIND3D
+    from oracle import cform
+    x = synth_volume(shape, 77 + delta).cuda()
+    noise = torch.randn((shape[0], 12) + shape[2:], device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    m = MIND3D(delta=delta)
+    monkeypatch.delenv("DGTTA_MIND_NO_TMA", raising=False)
+    a = m(x, noise=noise)
+    assert torch.equal(a, m(x, noise=noise))
+    monkeypatch.setenv("DGTTA_MIND_NO_TMA", "1")
+    b = m(x, noise=noise)
+    assert torch.equal(a, b)
+    if x.numel() <= 128 ** 3:
+        ref = cform.mind_ssc(x.cpu().numpy(), delta=delta, noise=noise.cpu().numpy())
+        assert np.abs(a.cpu().numpy() - ref).max() <= TOL
+
+
+def test_full_size_with_noise_against_oracle():
+    """BASELINE configs[0] (1x1x128^3, delta 2) with the reference's default noise weight against the C oracle."""
+    from dg_tta_b200 import MIND3D
+    from oracle import cform
+    shape = (1, 1, 128, 128, 128)
+    x = synth_volume(shape, 4321)
+    noise = torch.randn((1, 12, 128, 128, 128), generator=torch.Generator().manual_seed(2))
+    out = MIND3D(delta=2)(x.cuda(), noise=noise.cuda()).cpu().numpy()
+    ref = cform.mind_ssc(x.numpy(), delta=2, noise=noise.numpy())
+    assert np.abs(out - ref).max() <= TOL
+    assert (out.max(1) == 1.0).all() and (out > 0).all()

@@ -29,6 +29,7 @@ def timeit(fn, iters=10, warm=3):
 
 def main():
     res = {}
+    only = sys.argv[1] if len(sys.argv) > 1 else ""   # "mind": MIND timings only
     for shape in [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]:
         x = synth_volume(shape, 1).cuda()
         vox = x.numel()
@@ -40,6 +41,10 @@ def main():
         res[f"mind_noise_tensor_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6, gbs=vox * 100 / med / 1e6)
         med, best = timeit(lambda: mind_ssc(x))
         res[f"mind_default_randn_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6)
+    if only == "mind":
+        for k, v in res.items():
+            print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
+        return
     x = synth_volume((2, 1, 192, 192, 192), 2).cuda()
     net = GINGroupConv(dict(IN_CHANNELS=1, N_LAYER=4, INTERM_CHANNELS=2))
     for want in ([1, 1, 1, 1], [3, 3, 3, 3], [3, 1, 3, 1]):
