@@ -34,9 +34,16 @@ namespace fast {
 constexpr int NOISE_TMA = 3;
 
 constexpr int R = 2, NT = 5, PB = 4, NWIN = NT - 1;   // PB == NWIN keeps the D-window slots compile-time
-constexpr int EH = MIND_TH + 2 * R;   // 20 halo rows
-constexpr int C_WARPS = MIND_TH;           // 16 warps own the patch rows in stage C
-constexpr int NTHREADS = MIND_THREADS;     // 512
+// Patch rows per CTA.  16 rows = one 512-thread CTA per SM; 8 rows = two independent 256-thread CTAs per SM whose
+// shared-memory-bound phases (S1, S2) overlap the other CTA's FP32-bound phase (C) at the price of more halo rows.
+#ifndef DGTTA_FAST_TH
+#define DGTTA_FAST_TH 16
+#endif
+constexpr int TH = DGTTA_FAST_TH, TW = MIND_TW;
+constexpr int CTAS_PER_SM = TH == 16 ? 1 : 2;
+constexpr int EH = TH + 2 * R;             // halo rows: 20 / 12
+constexpr int C_WARPS = TH;                // one warp per patch row in stage C
+constexpr int NTHREADS = TH * 32;          // 512 / 256
 
 // Halo-tile geometry per noise mode.  LDG modes: 36 halo columns [w0-2, w0+34), ws channel pitch 740 words = 185
 // 16-byte chunks == 1 (mod 8) so that consecutive S2 tasks (9 strips per channel) stay conflict-free.  TMA mode: 40
@@ -44,16 +51,17 @@ constexpr int NTHREADS = MIND_THREADS;     // 512
 template <int NOISE> struct Mode {
     static constexpr bool TMA = NOISE == NOISE_TMA;
     static constexpr int CO = TMA ? 4 : R;             // halo column 0 is w0 - CO
-    static constexpr int EW = MIND_TW + 2 * CO;        // halo columns: 40 / 36
+    static constexpr int EW = TW + 2 * CO;        // halo columns: 40 / 36
     static constexpr int NQUAD = EW / 4;               // position quads per halo row: 10 / 9
     static constexpr int TWD = EW + 8;                 // image tile row pitch: 4 pad + EW + 4 pad words
     static constexpr int WSP = EW;                     // ws row pitch
     static constexpr int WS_CH = TMA ? EH * WSP : EH * WSP + 20;
     static constexpr int WS_PLANE = 12 * WS_CH;
-    static constexpr int NSW = TMA ? PB + 1 : PB;      // ws plane ring: one spare plane lets noise of the next batch fly under C
+    // ws plane ring: with one CTA per SM a spare plane lets noise of the next batch fly under C; with two the other
+    // CTA covers the wait and the shared memory is needed for residency
+    static constexpr int NSW = TMA && CTAS_PER_SM == 1 ? PB + 1 : PB;
     static constexpr int S1_TASKS = PB * EH * NQUAD;   // 800 / 720
-    static constexpr int S2_TASKS = PB * 12 * NQUAD;   // 480 / 432 column-strip tasks: a single round
-    static_assert(S2_TASKS <= NTHREADS, "S2 must fit one round");
+    static constexpr int S2_TASKS = PB * 12 * NQUAD;   // 480 / 432 column-strip tasks
 };
 
 template <int DELTA, int NOISE>
@@ -79,7 +87,7 @@ struct Params {
     const float *fix_lohi;
     int B, D, H, W;
     int nTH, nTW, nCD, chunkD, nbatch;
-    int stagger;          // cycles: CTA i starts (i mod 4) * stagger late so that the SMs' store phases do not coincide
+    int stagger, sms;     // cycles by which the second resident CTA of an SM starts late (phase offset between the two)
     float rw;
     float taps[NT];
 };
@@ -420,10 +428,11 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 
         // ================= S2: H smoothing of a 4-column strip, in place, sliding 5-row register window
         // one (plane, channel, column quad) task per thread, exactly one round
-        const int s2_t = opaque(tid);
+#pragma unroll 1
+        for (int s2_t = opaque(tid); s2_t < S2_TASKS; s2_t += NTHREADS) {
         const int s2_pc = s2_t / NQUAD;                  // pz * 12 + c
         const int s2_pz = s2_pc / 12;
-        if (s2_t < S2_TASKS && zb + s2_pz < z_end) {
+        if (zb + s2_pz < z_end) {
             float *col = ws + slot_of(s2_pz) * WS_PLANE + (s2_pc - s2_pz * 12) * WS_CH + 4 * (s2_t - s2_pc * NQUAD);
             u64 acc[NT][2];   // partial sums of the 5 output rows that input row r contributes to
 #pragma unroll
@@ -434,13 +443,14 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const int o = r - t;
-                    if (o < 0 || o >= MIND_TH) continue;
+                    if (o < 0 || o >= TH) continue;
                     if (t == 0) { acc[o % NT][0] = fmul2(x0, G2[0]); acc[o % NT][1] = fmul2(x1, G2[0]); }
                     else { acc[o % NT][0] = ffma2(x0, G2[t], acc[o % NT][0]); acc[o % NT][1] = ffma2(x1, G2[t], acc[o % NT][1]); }
                 }
                 const int done = r - (NT - 1);
                 if (done >= 0) st4p(col + done * WSP, acc[done % NT][0], acc[done % NT][1]);   // row `done` is dead as an input
             }
+        }
         }
         __syncthreads();   // ws complete; tiles no longer read in this batch
 
@@ -594,8 +604,12 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         }
         if (TMA) {
             // the batch consumed one fill of each of its PB slots; the next batch starts PB slots further round the ring
-            fill_parity ^= ((1u << NSW) - 1u) ^ (1u << slot_of(PB));
-            slot0 = slot_of(PB);
+            if (NSW > PB) {
+                fill_parity ^= ((1u << NSW) - 1u) ^ (1u << slot_of(PB));
+                slot0 = slot_of(PB);
+            } else {
+                fill_parity ^= (1u << NSW) - 1u;
+            }
         }
     }
     if (!FIX) {
@@ -626,13 +640,13 @@ __device__ __forceinline__ void decode_cta(const Params &P, int cta, int &b, int
     const int tw = cta % P.nTW; cta /= P.nTW;
     const int th = cta % P.nTH; cta /= P.nTH;
     b = cta;
-    h0 = th * MIND_TH; w0 = tw * MIND_TW;
+    h0 = th * TH; w0 = tw * TW;
     d0 = cd * P.chunkD;
     d1 = min(P.D, d0 + P.chunkD);
 }
 
 template <int DELTA, int NOISE>
-__global__ void __launch_bounds__(NTHREADS, 1) mind_fast_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(128) float smem[];
     __shared__ float red[3][C_WARPS];
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mind_fast_kernel(const __grid_con
     int b, h0, w0, d0, d1;
     decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
     if (P.stagger > 0) {
-        const long long t0 = clock64(), wait = (long long)(blockIdx.x & 3) * P.stagger;
+        const long long t0 = clock64(), wait = (long long)((blockIdx.x / P.sms) & 1) * P.stagger;
         while (clock64() - t0 < wait) {}
     }
     process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, b, h0, w0, d0, d1, 0.f, 0.f,
@@ -650,7 +664,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mind_fast_kernel(const __grid_con
 
 // pass 2: persistent CTAs walk the list of (CTA, batch) units whose clamp is active
 template <int DELTA, int NOISE>
-__global__ void __launch_bounds__(NTHREADS, 1) mind_fast_fix_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_fix_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(128) float smem[];
     __shared__ float red[3][C_WARPS];
@@ -709,13 +723,13 @@ struct Plan {
 static Plan make_plan(int B, int D, int H, int W)
 {
     Plan p;
-    p.nTH = (H + MIND_TH - 1) / MIND_TH;
-    p.nTW = (W + MIND_TW - 1) / MIND_TW;
+    p.nTH = (H + TH - 1) / TH;
+    p.nTW = (W + TW - 1) / TW;
     const long base = (long)B * p.nTH * p.nTW;
     // One CTA per SM is resident.  Choose the number of D chunks that minimises
     //   waves * (planes marched per CTA, rounded up to whole batches, + fixed per-CTA cost):
     // splitting D fills idle SMs but every chunk re-marches 2R warm-up planes.
-    const int sms = sm_count();
+    const int sms = sm_count() * CTAS_PER_SM;
     const int max_chunks = (D + 15) / 16;
     long best_cost = -1;
     int best = 1;
@@ -759,7 +773,7 @@ static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStrea
     mind_fast_finalize<<<1, 1024, 0, stream>>>(P.stats, nunits, 1.0 / ((double)P.B * P.D * P.H * P.W), hdr, lohi);
     rc = check_launch("mind_fast_finalize");
     if (rc) return rc;
-    mind_fast_fix_kernel<DELTA, NOISE><<<sm_count(), NTHREADS, G::SMEM, stream>>>(P);
+    mind_fast_fix_kernel<DELTA, NOISE><<<sm_count() * CTAS_PER_SM, NTHREADS, G::SMEM, stream>>>(P);
     return check_launch("mind_fast_fix_kernel");
 }
 
@@ -804,7 +818,9 @@ template <int DELTA>
 static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
 {
     if (noise_mode == DGTTA_NOISE_TENSOR) {
-        if (DELTA <= 2 && make_noise_map(P)) return launch<DELTA <= 2 ? DELTA : 1, NOISE_TMA>(P, plan, workspace, stream);
+        constexpr int TMA_MAX_DELTA = CTAS_PER_SM == 1 ? 2 : 1;   // shared-memory budget
+        if (DELTA <= TMA_MAX_DELTA && make_noise_map(P))
+            return launch<DELTA <= TMA_MAX_DELTA ? DELTA : 1, NOISE_TMA>(P, plan, workspace, stream);
         return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
     }
     return launch<DELTA, DGTTA_NOISE_NONE>(P, plan, workspace, stream);
@@ -821,7 +837,7 @@ bool mind_fast_supported(const MindArgs &a)
 size_t mind_fast_workspace_bytes(int B, int D, int H, int W)
 {
     // bound independent of the SM count: chunks are >= 16 planes (or the whole of D)
-    const size_t nTH = (H + MIND_TH - 1) / MIND_TH, nTW = (W + MIND_TW - 1) / MIND_TW;
+    const size_t nTH = (H + fast::TH - 1) / fast::TH, nTW = (W + fast::TW - 1) / fast::TW;
     const size_t max_chunks = (D + 15) / 16;
     // per chunk at most ceil((chunkD + 4)/5) batches with chunkD <= D; bound the product generously
     const size_t units = (size_t)B * nTH * nTW * ((size_t)D / fast::PB + 3 * max_chunks + 2);
@@ -844,7 +860,7 @@ int mind_fast_launch(const MindArgs &a, cudaStream_t stream)
     P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W;
     P.nTH = plan.nTH; P.nTW = plan.nTW; P.nCD = plan.nCD; P.chunkD = plan.chunkD; P.nbatch = plan.nbatch;
     P.rw = a.rw;
-    { const char *e = getenv("DGTTA_MIND_STAGGER"); P.stagger = e ? atoi(e) : 0; }
+    { const char *e = getenv("DGTTA_MIND_STAGGER"); P.stagger = e ? atoi(e) : 0; P.sms = sm_count(); }
     for (int i = 0; i < fast::NT; ++i) P.taps[i] = a.taps[i];
     switch (a.delta) {
         case 1: return fast::launch_noise<1>(P, plan, a.workspace, a.noise_mode, stream);

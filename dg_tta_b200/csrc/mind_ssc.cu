@@ -12,6 +12,11 @@
 
 using namespace dgtta;
 
+namespace dgtta {
+int philox_normal_fill(float *out, unsigned long long numel, unsigned long long seed, unsigned long long offset, int sms,
+                       int max_threads_per_sm, cudaStream_t stream);   // philox_normal.cu
+}
+
 extern "C" size_t dgtta_mind_workspace_bytes(int B, int D, int H, int W)
 {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
@@ -36,7 +41,6 @@ extern "C" int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const fl
                                   uint64_t philox_seed, uint64_t philox_offset, void *workspace_dev,
                                   size_t workspace_bytes, dgtta_stream_t stream)
 {
-    (void)philox_seed; (void)philox_offset;
     if (!img_dev || !out_dev || !taps_host || !workspace_dev) { set_error("dgtta_mind_ssc_fwd: null pointer"); return DGTTA_ENULL; }
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || delta < 1 || ntaps < 3 || ntaps > 9 || !(ntaps & 1)) {
         set_error("dgtta_mind_ssc_fwd: bad shape/params B=%d D=%d H=%d W=%d delta=%d ntaps=%d", B, D, H, W, delta, ntaps);
@@ -46,11 +50,25 @@ extern "C" int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const fl
         set_error("dgtta_mind_ssc_fwd: volume too large");
         return DGTTA_EINVAL;
     }
-    if (noise_mode != DGTTA_NOISE_NONE && noise_mode != DGTTA_NOISE_TENSOR) {
+    if (noise_mode != DGTTA_NOISE_NONE && noise_mode != DGTTA_NOISE_TENSOR && noise_mode != DGTTA_NOISE_PHILOX) {
         set_error("dgtta_mind_ssc_fwd: noise_mode %d not supported", noise_mode);
         return DGTTA_EUNSUPPORTED;
     }
-    if (noise_mode == DGTTA_NOISE_TENSOR && !noise_dev) { set_error("dgtta_mind_ssc_fwd: noise tensor missing"); return DGTTA_ENULL; }
+    if (noise_mode != DGTTA_NOISE_NONE && !noise_dev) { set_error("dgtta_mind_ssc_fwd: noise tensor / scratch missing"); return DGTTA_ENULL; }
+    if (noise_mode == DGTTA_NOISE_PHILOX) {
+        // regenerate torch.randn_like(edge_selection) for generator state (seed, offset) into the caller's scratch,
+        // then run the streamed-noise kernel on it
+        int dev = 0, mt = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&mt, cudaDevAttrMaxThreadsPerMultiProcessor, dev) != cudaSuccess) {
+            set_error("dgtta_mind_ssc_fwd: device query failed");
+            return (int)cudaGetLastError();
+        }
+        const int rc = philox_normal_fill(const_cast<float *>(noise_dev), (unsigned long long)B * 12 * D * H * W, philox_seed,
+                                          philox_offset, sm_count(), mt, (cudaStream_t)stream);
+        if (rc) return rc;
+        noise_mode = DGTTA_NOISE_TENSOR;
+    }
     if ((uintptr_t)workspace_dev & 15) { set_error("dgtta_mind_ssc_fwd: workspace must be 16-byte aligned"); return DGTTA_EWORKSPACE; }
     MindArgs a;
     a.img = img_dev; a.out = out_dev; a.noise = noise_dev; a.in_scale = in_scale_dev;

@@ -1,0 +1,92 @@
+// N(0,1) field of MIND3D's edge noise (dg_tta/mind.py:150, torch.randn_like(edge_selection)) regenerated on the
+// device, bit-identical to what torch's CUDA generator writes for the same (seed, offset).
+//
+// torch (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy + distribution_elementwise_grid_stride_kernel
+// with curand_normal4) launches G = min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)) blocks of 256 threads; with
+// T = 256 G, thread idx < T initialises Philox4x32-10 with (key = seed, subsequence = idx, offset) and its j-th
+// engine call fills elements  idx + T (4 j + ii), ii = 0..3  with the four Box-Muller normals of that call.  For an
+// offset that is a multiple of 4 (torch only ever advances it by multiples of 4) the j-th call is the Philox block
+// with counter (offset / 4 + j, idx).  Here every (idx, j) pair is an independent work item: no per-thread generator
+// state, no wasted look-ahead block, four coalesced 128-byte stores per warp and pair.  The integer rounds and the
+// Box-Muller transform are the CUDA toolkit's own inline device functions (curand_philox4x32_x.h, curand_normal.h) —
+// the arithmetic torch runs — so equality is by construction, and tests/test_philox_gpu.py checks it bitwise.
+#include <curand_kernel.h>
+
+#include "common.cuh"
+
+namespace dgtta {
+
+namespace philox {
+
+constexpr int BLOCK = 256;   // torch's block_size_bound: part of the stream's definition, not a tuning knob
+constexpr int JB = 4;        // engine calls per thread
+
+__global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ out, unsigned long long numel,
+                                                            unsigned long long T, uint2 key, unsigned long long ctr0,
+                                                            int J)
+{
+    const unsigned long long idx = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;   // < T
+    const int j0 = blockIdx.y * JB;
+#pragma unroll
+    for (int jj = 0; jj < JB; ++jj) {
+        const int j = j0 + jj;
+        if (j >= J) break;
+        const unsigned long long c = ctr0 + (unsigned long long)j;
+        const uint4 ctr = make_uint4((unsigned)c, (unsigned)(c >> 32), (unsigned)idx, (unsigned)(idx >> 32));
+        const uint4 r = curand_Philox4x32_10(ctr, key);
+        const float2 a = _curand_box_muller(r.x, r.y);
+        const float2 b = _curand_box_muller(r.z, r.w);
+        unsigned long long li = idx + T * 4ull * (unsigned long long)j;
+        if (li < numel) __stcs(out + li, a.x);
+        li += T;
+        if (li < numel) __stcs(out + li, a.y);
+        li += T;
+        if (li < numel) __stcs(out + li, b.x);
+        li += T;
+        if (li < numel) __stcs(out + li, b.y);
+    }
+}
+
+}  // namespace philox
+
+// shared with mind_ssc.cu (DGTTA_NOISE_PHILOX)
+int philox_normal_fill(float *out, unsigned long long numel, unsigned long long seed, unsigned long long offset, int sms,
+                       int max_threads_per_sm, cudaStream_t stream)
+{
+    if (numel == 0) return 0;
+    if (!out) { set_error("dgtta_philox_normal_fill: null pointer"); return DGTTA_ENULL; }
+    if (offset & 3ull) { set_error("dgtta_philox_normal_fill: generator offset %llu is not a multiple of 4", offset); return DGTTA_EUNSUPPORTED; }
+    if (numel >= (1ull << 31)) {
+        // torch splits tensors that need 64-bit indexing into several launches with their own offsets
+        set_error("dgtta_philox_normal_fill: %llu elements need torch's split launches (not reproduced)", numel);
+        return DGTTA_EUNSUPPORTED;
+    }
+    if (sms <= 0 || max_threads_per_sm < philox::BLOCK) { set_error("dgtta_philox_normal_fill: bad device properties"); return DGTTA_EINVAL; }
+    unsigned long long G = (numel + philox::BLOCK - 1) / philox::BLOCK;
+    const unsigned long long cap = (unsigned long long)sms * (unsigned long long)(max_threads_per_sm / philox::BLOCK);
+    if (G > cap) G = cap;
+    const unsigned long long T = G * philox::BLOCK;
+    const int J = (int)((numel - 1) / (T * 4ull) + 1);
+    const dim3 grid((unsigned)G, (unsigned)((J + philox::JB - 1) / philox::JB));
+    philox::normal_fill_kernel<<<grid, philox::BLOCK, 0, stream>>>(out, numel, T, make_uint2((unsigned)seed, (unsigned)(seed >> 32)),
+                                                                   offset / 4ull, J);
+    return check_launch("philox_normal_fill_kernel");
+}
+
+}  // namespace dgtta
+
+extern "C" int dgtta_philox_normal_fill(float *out_dev, uint64_t numel, uint64_t philox_seed, uint64_t philox_offset,
+                                        int sm_count, int max_threads_per_sm, dgtta_stream_t stream)
+{
+    return dgtta::philox_normal_fill(out_dev, numel, philox_seed, philox_offset, sm_count, max_threads_per_sm,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" uint64_t dgtta_philox_normal_offset_increment(uint64_t numel, int sm_count, int max_threads_per_sm)
+{
+    if (numel == 0 || sm_count <= 0 || max_threads_per_sm < dgtta::philox::BLOCK) return 0;
+    uint64_t G = (numel + dgtta::philox::BLOCK - 1) / dgtta::philox::BLOCK;
+    const uint64_t cap = (uint64_t)sm_count * (uint64_t)(max_threads_per_sm / dgtta::philox::BLOCK);
+    if (G > cap) G = cap;
+    return ((numel - 1) / (dgtta::philox::BLOCK * G * 4) + 1) * 4;   // calc_execution_policy: engine calls * 4
+}

@@ -10,7 +10,7 @@ import torch
 
 from .. import _lib
 from ..gin import GINGroupConv, _GIN_CFG
-from ..mind import mind_ssc
+from ..mind import mind_ssc, randn_like_reference
 
 _INTERP = {"bilinear": 0, "nearest": 1}
 _PAD = {"zeros": 0, "border": 1}
@@ -111,7 +111,7 @@ def gin_mind_aug(input):
         side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
     side.wait_stream(main)                                    # generator/allocator ordering with earlier work
     with torch.cuda.stream(side):
-        noise = torch.randn((B, 12, D, H, W), device=dev, dtype=torch.float32)
+        noise = randn_like_reference((B, 12, D, H, W), dev)   # == torch.randn(...), generated by our Philox kernel
     from ..gin import gin_forward
     mixed, scale = gin_forward(input, kers, shifts, alphas, net.interm_channel, defer_scale=True)
     main.wait_stream(side)

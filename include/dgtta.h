@@ -35,7 +35,7 @@ typedef struct CUstream_st *dgtta_stream_t; /* == cudaStream_t */
 /* MIND noise source (dg_tta/mind.py:150-152) */
 #define DGTTA_NOISE_NONE 0   /* randn_weighting ignored: E = I(p+s1) - I(p+s2)            */
 #define DGTTA_NOISE_TENSOR 1 /* noise_dev holds the [B,12,D,H,W] normal field              */
-#define DGTTA_NOISE_PHILOX 2 /* regenerate torch's CUDA randn stream in-kernel (seed, offset) */
+#define DGTTA_NOISE_PHILOX 2 /* regenerate torch's CUDA randn stream on the device from (seed, offset) */
 
 /* sampler modes (torch.nn.functional.grid_sample arguments used at tta.py:549,573; torch_utils.py:59,71) */
 #define DGTTA_INTERP_TRILINEAR 0
@@ -56,8 +56,10 @@ uint64_t dgtta_launch_count(void);
  *   in_scale_dev: NULL, or [B,2] floats (a_b, c_b): the kernel reads I = (img * a_b) * c_b — the
  *                 deferred Frobenius re-normalisation of GIN (gin.py:228) when GIN feeds MIND.
  *   taps_host [ntaps] Gaussian taps (mind.py:27-37), ntaps odd, 1..9
- *   noise_mode/noise_dev/philox_*: see DGTTA_NOISE_*.  For PHILOX, (seed, offset) are the device
- *                 generator's state before the draw; the caller advances the generator by
+ *   noise_mode/noise_dev/philox_*: see DGTTA_NOISE_*.  For PHILOX, noise_dev is a caller-owned scratch
+ *                 of B*12*D*H*W floats that the call fills with the field torch.randn_like(edge_selection)
+ *                 (mind.py:150) draws for the device generator state (seed, offset) before the draw
+ *                 (dgtta_philox_normal_fill), and the caller advances the generator by
  *                 dgtta_mind_philox_offset_increment() afterwards.
  *   workspace: dgtta_mind_workspace_bytes(B,D,H,W) bytes, 16-byte aligned.
  * Two launches: a speculative fused stencil pass that also reduces the statistics of the
@@ -73,6 +75,15 @@ int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const float *in_sca
  * (ATen/native/cuda/DistributionTemplates.h calc_execution_policy); sm_count/max_threads_per_sm
  * are the device properties torch uses. */
 uint64_t dgtta_mind_philox_offset_increment(int B, int D, int H, int W, int sm_count, int max_threads_per_sm);
+
+/* The N(0,1) field torch.randn(numel elements, device="cuda") writes for generator state (seed, offset):
+ * Philox4x32-10 + Box-Muller in torch's element order (ATen/native/cuda/DistributionTemplates.h), the
+ * draw behind mind.py:150.  offset must be a multiple of 4 and numel < 2^31 (torch's single-launch case);
+ * sm_count / max_threads_per_sm are the device properties torch derives its grid from.
+ * dgtta_philox_normal_offset_increment: how far that draw advances the generator offset. */
+int dgtta_philox_normal_fill(float *out_dev, uint64_t numel, uint64_t philox_seed, uint64_t philox_offset,
+                             int sm_count, int max_threads_per_sm, dgtta_stream_t stream);
+uint64_t dgtta_philox_normal_offset_increment(uint64_t numel, int sm_count, int max_threads_per_sm);
 
 /* ---------------------------------------------------------------------------------------------
  * GIN augmentation.  Replaces GINGroupConv.forward (dg_tta/gin.py:168-230) and the per-layer

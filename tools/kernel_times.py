@@ -41,6 +41,12 @@ def main():
         res[f"mind_noise_tensor_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6, gbs=vox * 100 / med / 1e6)
         med, best = timeit(lambda: mind_ssc(x))
         res[f"mind_default_randn_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6)
+    from dg_tta_b200.mind import randn_like_reference
+    for shape in [(2, 12, 192, 192, 192)]:
+        med, best = timeit(lambda: torch.randn(shape, device="cuda"))
+        res["torch_randn_2x12x192"] = dict(ms=med, best=best, gbs=2 * 12 * 192 ** 3 * 4 / med / 1e6)
+        med, best = timeit(lambda: randn_like_reference(shape, "cuda"))
+        res["ours_philox_normal_2x12x192"] = dict(ms=med, best=best, gbs=2 * 12 * 192 ** 3 * 4 / med / 1e6)
     if only == "mind":
         for k, v in res.items():
             print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
