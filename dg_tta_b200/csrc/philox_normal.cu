@@ -7,9 +7,10 @@
 // engine call fills elements  idx + T (4 j + ii), ii = 0..3  with the four Box-Muller normals of that call.  For an
 // offset that is a multiple of 4 (torch only ever advances it by multiples of 4) the j-th call is the Philox block
 // with counter (offset / 4 + j, idx).  Here every (idx, j) pair is an independent work item: no per-thread generator
-// state, no wasted look-ahead block, four coalesced 128-byte stores per warp and pair.  The integer rounds and the
-// Box-Muller transform are the CUDA toolkit's own inline device functions (curand_philox4x32_x.h, curand_normal.h) —
-// the arithmetic torch runs — so equality is by construction, and tests/test_philox_gpu.py checks it bitwise.
+// state, no wasted look-ahead block, round keys in the constant bank, 32-bit offsets, bounds checks only in the last
+// engine call, four coalesced 128-byte stores per warp and pair.  The Box-Muller transform is the CUDA toolkit's own
+// inline device function (curand_normal.h: the float arithmetic torch runs); tests/test_philox_gpu.py checks the
+// stream bitwise against torch.randn.
 #include <curand_kernel.h>
 
 #include "common.cuh"
@@ -21,29 +22,48 @@ namespace philox {
 constexpr int BLOCK = 256;   // torch's block_size_bound: part of the stream's definition, not a tuning knob
 constexpr int JB = 4;        // engine calls per thread
 
-__global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ out, unsigned long long numel,
-                                                            unsigned long long T, uint2 key, unsigned long long ctr0,
-                                                            int J)
+struct Keys {
+    unsigned k[10][2];   // Philox4x32-10 round keys (key + r * Weyl constants): uniform, so they live in the constant bank
+};
+
+// One Philox4x32-10 block (the integer function behind curand_Philox4x32_10; Salmon et al., SC'11): per round two
+// 32x32->64 multiplies and two 3-input xors.
+__device__ __forceinline__ uint4 philox10(uint4 c, const Keys &K)
 {
-    const unsigned long long idx = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;   // < T
-    const int j0 = blockIdx.y * JB;
 #pragma unroll
-    for (int jj = 0; jj < JB; ++jj) {
-        const int j = j0 + jj;
-        if (j >= J) break;
-        const unsigned long long c = ctr0 + (unsigned long long)j;
-        const uint4 ctr = make_uint4((unsigned)c, (unsigned)(c >> 32), (unsigned)idx, (unsigned)(idx >> 32));
-        const uint4 r = curand_Philox4x32_10(ctr, key);
-        const float2 a = _curand_box_muller(r.x, r.y);
-        const float2 b = _curand_box_muller(r.z, r.w);
-        unsigned long long li = idx + T * 4ull * (unsigned long long)j;
-        if (li < numel) __stcs(out + li, a.x);
-        li += T;
-        if (li < numel) __stcs(out + li, a.y);
-        li += T;
-        if (li < numel) __stcs(out + li, b.x);
-        li += T;
-        if (li < numel) __stcs(out + li, b.y);
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
+        c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ K.k[r][0], (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ K.k[r][1], (unsigned)p0);
+    }
+    return c;
+}
+
+template <bool TAIL>
+__device__ __forceinline__ void one_call(float *__restrict__ out, unsigned numel, unsigned T, unsigned idx, unsigned long long c,
+                                         int j, const Keys &K)
+{
+    const uint4 r = philox10(make_uint4((unsigned)c, (unsigned)(c >> 32), idx, 0u), K);
+    const float2 a = _curand_box_muller(r.x, r.y);   // curand_normal.h: the float arithmetic torch's curand_normal4 runs
+    const float2 b = _curand_box_muller(r.z, r.w);
+    const unsigned li = idx + T * 4u * (unsigned)j;   // numel < 2^31 and li < numel + 4T: 32-bit offsets suffice
+    if (!TAIL || li < numel) __stcs(out + li, a.x);
+    if (!TAIL || li + T < numel) __stcs(out + li + T, a.y);
+    if (!TAIL || li + 2u * T < numel) __stcs(out + li + 2u * T, b.x);
+    if (!TAIL || li + 3u * T < numel) __stcs(out + li + 3u * T, b.y);
+}
+
+__global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ out, unsigned numel, unsigned T,
+                                                            const __grid_constant__ Keys K, unsigned long long ctr0, int J)
+{
+    const unsigned idx = blockIdx.x * BLOCK + threadIdx.x;   // < T
+    const int j0 = blockIdx.y * JB;
+    if (j0 + JB < J) {
+        // every engine call but the last writes four in-range elements: no bounds checks
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) one_call<false>(out, numel, T, idx, ctr0 + (unsigned long long)(j0 + jj), j0 + jj, K);
+    } else {
+        for (int j = j0; j < J; ++j) one_call<true>(out, numel, T, idx, ctr0 + (unsigned long long)j, j, K);
     }
 }
 
@@ -68,8 +88,12 @@ int philox_normal_fill(float *out, unsigned long long numel, unsigned long long 
     const unsigned long long T = G * philox::BLOCK;
     const int J = (int)((numel - 1) / (T * 4ull) + 1);
     const dim3 grid((unsigned)G, (unsigned)((J + philox::JB - 1) / philox::JB));
-    philox::normal_fill_kernel<<<grid, philox::BLOCK, 0, stream>>>(out, numel, T, make_uint2((unsigned)seed, (unsigned)(seed >> 32)),
-                                                                   offset / 4ull, J);
+    philox::Keys K;
+    for (int r = 0; r < 10; ++r) {
+        K.k[r][0] = (unsigned)seed + (unsigned)r * 0x9E3779B9u;
+        K.k[r][1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u;
+    }
+    philox::normal_fill_kernel<<<grid, philox::BLOCK, 0, stream>>>(out, (unsigned)numel, (unsigned)T, K, offset / 4ull, J);
     return check_launch("philox_normal_fill_kernel");
 }
 
