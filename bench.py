@@ -52,6 +52,24 @@ def synth_volume(shape, seed):
     return x.clamp(-1.85, 2.75).contiguous()
 
 
+def committed_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one mind_fast_kernel launch (noise streamed in, 2x1x192^3) from
+    the newest ncu --set full summary committed under profiles/ (bytes, per launch); None if there is none."""
+    import re
+    best = None
+    for path in sorted((ROOT / "profiles").glob("*_mind_noise_ncu_summary.txt")):
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(rf"{re.escape(key)}\s+([0-9.]+)\s+(\w+)", path.read_text())
+            if not m:
+                tot = None
+                break
+            tot += float(m.group(1)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), float("nan"))
+        if tot:
+            best = (tot, path.name)
+    return best
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -178,6 +196,13 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     sync_all()
+    # untimed settling on top of the W warm-up steps: a box that has just been idle (or under a profiler) needs a few
+    # hundred ms under load before SM clocks and the allocator's block pool are in steady state
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < 0.4:
+        step(0)
+        torch.cuda.synchronize()
+    sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -256,6 +281,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     achieved = MIND_BYTES_PER_VOXEL_NOISE * vox_step / (mind_kernel_ms * 1e-3) / 1e9
+    traffic = committed_dram_traffic()
 
     # CPU baseline: the torch-CPU port on a bounded slab of the same batch (~15 s of CPU work)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -272,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gin_mind_aug (GIN 4-layer random conv stack + blend + Frobenius renorm -> MIND-SSC delta=1 "
-                               "sigma=1 with torch.randn edge noise) on 2x1x192x192x192 fp32 per GPU (BASELINE.json "
+                               "sigma=1 with the torch.randn edge noise regenerated by the library's Philox kernel) on 2x1x192x192x192 fp32 per GPU (BASELINE.json "
                                "configs[1] shape)",
                    "l2": "3 rotating input batches; per-step working set 1.4 GB >> 126 MB L2",
                    "seeds": "torch.manual_seed(step) -> GIN kernel sizes/weights identical to the reference arm",
@@ -281,10 +307,12 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": h_out[0].numel() * 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "dg_tta_b200.host_pipeline.HostPipeline.submit (H2D / transform / D2H of consecutive steps overlapped)"},
-        "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (torch.randn's launch not counted)
-        "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1,noise=tensor> (+finalize, fix-up)",
+        "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (counted inside the library)
+        "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1,noise=TMA-staged tensor> (+finalize, fix-up)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic[0] if traffic else None,
+                     "traffic_source": f"profiles/{traffic[1]} (ncu --set full, dram read+write bytes per launch)" if traffic else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_voxel": MIND_BYTES_PER_VOXEL_NOISE, "kernel_ms": mind_kernel_ms},
         "cpu_baseline": {"value": sample.numel() / cpu_dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"one gin_mind_aug step on the first {depth} of 192 D-planes (2x1x{depth}x192x192)"},

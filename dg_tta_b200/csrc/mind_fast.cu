@@ -87,7 +87,6 @@ struct Params {
     const float *fix_lohi;
     int B, D, H, W;
     int nTH, nTW, nCD, chunkD, nbatch;
-    int stagger, sms;     // cycles by which the second resident CTA of an SM starts late (phase offset between the two)
     float rw;
     float taps[NT];
 };
@@ -654,10 +653,6 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const 
     __shared__ uint64_t empty_bar[PB + 1];
     int b, h0, w0, d0, d1;
     decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
-    if (P.stagger > 0) {
-        const long long t0 = clock64(), wait = (long long)((blockIdx.x / P.sms) & 1) * P.stagger;
-        while (clock64() - t0 < wait) {}
-    }
     process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, b, h0, w0, d0, d1, 0.f, 0.f,
                                  P.stats + (size_t)blockIdx.x * P.nbatch);
 }
@@ -860,7 +855,6 @@ int mind_fast_launch(const MindArgs &a, cudaStream_t stream)
     P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W;
     P.nTH = plan.nTH; P.nTW = plan.nTW; P.nCD = plan.nCD; P.chunkD = plan.chunkD; P.nbatch = plan.nbatch;
     P.rw = a.rw;
-    { const char *e = getenv("DGTTA_MIND_STAGGER"); P.stagger = e ? atoi(e) : 0; P.sms = sm_count(); }
     for (int i = 0; i < fast::NT; ++i) P.taps[i] = a.taps[i];
     switch (a.delta) {
         case 1: return fast::launch_noise<1>(P, plan, a.workspace, a.noise_mode, stream);

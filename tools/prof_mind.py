@@ -21,6 +21,10 @@ elif what == "mind_noise":
     n = torch.randn(2, 12, 192, 192, 192, device="cuda")
     for _ in range(3):
         mind_ssc(x, noise=n)
+elif what == "philox":
+    from dg_tta_b200.mind import randn_like_reference
+    for _ in range(3):
+        randn_like_reference((2, 12, 192, 192, 192), "cuda")
 elif what.startswith("gin"):
     from dg_tta_b200.gin import GINGroupConv, gin_forward
     want = [int(c) for c in what[3:]] if len(what) > 3 else [3, 3, 3, 3]
