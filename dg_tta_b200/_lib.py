@@ -19,6 +19,7 @@ SIGNATURES = {
     "dgtta_abi_version": (c_int, []),
     "dgtta_last_error": (c_char_p, []),
     "dgtta_launch_count": (c_uint64, []),
+    "dgtta_preload_kernels": (c_int, []),
     "dgtta_mind_workspace_bytes": (c_size_t, [c_int] * 4),
     "dgtta_mind_ssc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                    c_float, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
@@ -66,8 +67,17 @@ def check(rc, what):
         raise DgttaError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
 
 
+_preloaded = set()
+
+
 def stream_ptr():
+    """Current torch stream of the current device as a cudaStream_t.  Every operator passes through here, so this is
+    also where the library's kernels are loaded into a device's context the first time that device is used."""
     import torch
+    dev = torch.cuda.current_device()
+    if dev not in _preloaded:
+        _preloaded.add(dev)
+        check(lib().dgtta_preload_kernels(), "dgtta_preload_kernels")
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -187,6 +187,16 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const
     }
 }
 
+void preload_sampler()
+{
+    DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS>);
+    DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER>);
+    DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_ZEROS>);
+    DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_BORDER>);
+    DGTTA_TOUCH(affine_sample_bwd_kernel<DGTTA_PAD_ZEROS>);
+    DGTTA_TOUCH(affine_sample_bwd_kernel<DGTTA_PAD_BORDER>);
+}
+
 static int sample_check(const void *a, const void *t, const void *o, int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo)
 {
     if (!a || !t || !o) { set_error("dgtta_affine_sample: null pointer"); return DGTTA_ENULL; }

@@ -34,7 +34,29 @@ int sm_count()
 
 }  // namespace dgtta
 
-namespace dgtta { unsigned long long launches(); }
+namespace dgtta {
+unsigned long long launches();
+void preload_mind_fast();
+void preload_mind_general();
+void preload_gin();
+void preload_gin_fused();
+void preload_sampler();
+void preload_philox();
+}
+
+// CUDA loads kernels lazily, on their first launch (a few ms each).  GIN alone has 22 instantiations selected by the
+// random kernel sizes of a call, so without this a "warm" process still hits cold kernels for many steps.
+extern "C" int dgtta_preload_kernels(void)
+{
+    dgtta::preload_mind_fast();
+    dgtta::preload_mind_general();
+    dgtta::preload_gin();
+    dgtta::preload_gin_fused();
+    dgtta::preload_sampler();
+    dgtta::preload_philox();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
 extern "C" uint64_t dgtta_launch_count(void) { return dgtta::launches(); }
 extern "C" int dgtta_abi_version(void) { return DGTTA_ABI_VERSION; }
 extern "C" const char *dgtta_last_error(void) { return dgtta::g_err; }

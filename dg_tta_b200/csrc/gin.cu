@@ -156,6 +156,12 @@ __global__ void __launch_bounds__(256) gin_scale_kernel(float *out, const float 
 int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_host, const int *ks, const float *alphas_dev,
                      int B, int D, int H, int W, float *buf0, float *buf1, double *partials, cudaStream_t stream);
 
+void preload_gin()
+{
+    DGTTA_TOUCH(gin_layer_kernel<1>); DGTTA_TOUCH(gin_layer_kernel<3>);
+    DGTTA_TOUCH(gin_norm_kernel); DGTTA_TOUCH(gin_scale_kernel);
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct GinWorkspace {

@@ -308,6 +308,15 @@ __global__ void __launch_bounds__(256) gin_pointwise_kernel(const __grid_constan
     }
 }
 
+template <int CIN, int COUT>
+static void touch_conv()
+{
+    DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 0, false>); DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 0, true>);
+    DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 1, false>); DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 1, true>);
+    DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 2, false>); DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 2, true>);
+    DGTTA_TOUCH(gin_conv_seg_kernel<CIN, COUT, 3, true>);
+}
+
 static void fill_pointwise(Pointwise &L, const float *ker, const float *shift, int cin, int cout, int act)
 {
     for (int o = 0; o < 2; ++o) {
@@ -318,6 +327,12 @@ static void fill_pointwise(Pointwise &L, const float *ker, const float *shift, i
 }
 
 }  // namespace ginf
+
+void preload_gin_fused()
+{
+    ginf::touch_conv<1, 2>(); ginf::touch_conv<2, 2>(); ginf::touch_conv<2, 1>();
+    DGTTA_TOUCH(ginf::gin_pointwise_kernel);
+}
 
 // Runs the tuned path for cfg (1, 4, 2).  params_host layout as in dgtta_gin_fwd.  bufs: two device buffers of
 // B*2*V floats.  partials: [B][RED_SLOTS][2] doubles, zeroed by the caller.

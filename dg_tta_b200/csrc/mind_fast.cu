@@ -823,6 +823,22 @@ static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_
 
 }  // namespace fast
 
+template <int DELTA, int NOISE>
+static void touch_fast()
+{
+    DGTTA_TOUCH(fast::mind_fast_kernel<DELTA, NOISE>);
+    DGTTA_TOUCH(fast::mind_fast_fix_kernel<DELTA, NOISE>);
+}
+
+void preload_mind_fast()
+{
+    touch_fast<1, DGTTA_NOISE_NONE>(); touch_fast<2, DGTTA_NOISE_NONE>(); touch_fast<3, DGTTA_NOISE_NONE>();
+    touch_fast<1, DGTTA_NOISE_TENSOR>(); touch_fast<2, DGTTA_NOISE_TENSOR>(); touch_fast<3, DGTTA_NOISE_TENSOR>();
+    touch_fast<1, fast::NOISE_TMA>();
+    if (fast::CTAS_PER_SM == 1) touch_fast<fast::CTAS_PER_SM == 1 ? 2 : 1, fast::NOISE_TMA>();
+    DGTTA_TOUCH(fast::mind_fast_finalize);
+}
+
 bool mind_fast_supported(const MindArgs &a)
 {
     return a.ntaps == fast::NT && a.delta >= 1 && a.delta <= 3 &&

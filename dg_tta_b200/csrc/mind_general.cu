@@ -331,6 +331,20 @@ static int mind_dispatch_noise(const MindParams &P, int ntiles, cudaStream_t str
 }
 
 
+template <int R>
+static void touch_general()
+{
+    DGTTA_TOUCH(mind_general_kernel<R, false, DGTTA_NOISE_NONE>); DGTTA_TOUCH(mind_general_kernel<R, true, DGTTA_NOISE_NONE>);
+    DGTTA_TOUCH(mind_general_kernel<R, false, DGTTA_NOISE_TENSOR>); DGTTA_TOUCH(mind_general_kernel<R, true, DGTTA_NOISE_TENSOR>);
+}
+
+void preload_mind_general()
+{
+    // the reference's configuration (5 taps) runs in mind_fast.cu; of the general path only the 5-tap instance (large
+    // delta) is preloaded, the 3/7/9-tap instances keep CUDA's lazy loading
+    touch_general<2>();
+}
+
 size_t mind_general_workspace_bytes(int B, int D, int H, int W)
 {
     // upper bound independent of the SM count: at most ceil(D/16) chunks (see mind_plan)

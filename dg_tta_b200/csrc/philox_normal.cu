@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ 
 
 }  // namespace philox
 
+void preload_philox() { DGTTA_TOUCH(philox::normal_fill_kernel); }
+
 // shared with mind_ssc.cu (DGTTA_NOISE_PHILOX)
 int philox_normal_fill(float *out, unsigned long long numel, unsigned long long seed, unsigned long long offset, int sms,
                        int max_threads_per_sm, cudaStream_t stream)

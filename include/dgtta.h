@@ -47,6 +47,9 @@ int dgtta_abi_version(void);
 const char *dgtta_last_error(void);
 /* kernels launched by this library since the process started (diagnostics; bench.py's gpu_launches) */
 uint64_t dgtta_launch_count(void);
+/* Loads every kernel of the library into the current CUDA context (CUDA otherwise loads each kernel lazily at its
+ * first launch, a few ms apiece).  Call once per device after the context exists; 0 = ok. */
+int dgtta_preload_kernels(void);
 
 /* ---------------------------------------------------------------------------------------------
  * MIND-SSC descriptor.  Replaces MIND3D.forward (dg_tta/mind.py:142-164) including the shift
