@@ -27,10 +27,10 @@ namespace dgtta {
 namespace fast {
 
 // internal noise mode: DGTTA_NOISE_TENSOR whose field is staged by TMA (cp.async.bulk.tensor) straight into the
-// E^2 planes of shared memory, one 40 x 20 x 12-channel box per plane, and squared in place by S1.  TMA wants the
+// E^2 planes of shared memory, one 40 x 21 x 12-channel box per plane, and squared in place by S1.  TMA wants the
 // innermost start coordinate 16-byte aligned (measured: a start of w0-2 floats raises an illegal-instruction trap,
 // tools/microbench/tma_probe.cu), so this mode widens the halo tile to the aligned columns [w0-4, w0+36).  Needs
-// W % 4 == 0, a 16-byte aligned tensor and delta <= 2 (shared memory); everything else keeps the LDG path.
+// W % 4 == 0 and a 16-byte aligned tensor; everything else keeps the LDG path.
 constexpr int NOISE_TMA = 3;
 
 constexpr int R = 2, NT = 5, PB = 4, NWIN = NT - 1;   // PB == NWIN keeps the D-window slots compile-time
@@ -55,11 +55,15 @@ template <int NOISE> struct Mode {
     static constexpr int NQUAD = EW / 4;               // position quads per halo row: 10 / 9
     static constexpr int TWD = EW + 8;                 // image tile row pitch: 4 pad + EW + 4 pad words
     static constexpr int WSP = EW;                     // ws row pitch
-    static constexpr int WS_CH = TMA ? EH * WSP : EH * WSP + 20;
+    // TMA: the box carries one extra row so that the channel pitch is 21 * 10 = 210 chunks == 2 (mod 8): with 10 strips
+    // per channel, S2 task t = 10 c + s then hits chunk == t (mod 8) -> conflict-free (a dense 20-row box gives 200 == 0)
+    static constexpr int BOX_ROWS = TMA ? EH + 1 : EH;
+    static constexpr int WS_CH = TMA ? BOX_ROWS * WSP : EH * WSP + 20;
     static constexpr int WS_PLANE = 12 * WS_CH;
-    // ws plane ring: with one CTA per SM a spare plane lets noise of the next batch fly under C; with two the other
-    // CTA covers the wait and the shared memory is needed for residency
-    static constexpr int NSW = TMA && CTAS_PER_SM == 1 ? PB + 1 : PB;
+    // ws plane ring = the PB planes of a batch.  A spare fifth plane (noise of the next batch's first plane in flight
+    // during all of C) was measured slower (0.608 vs 0.589 ms): the ring arithmetic costs registers in stage C, and the
+    // last plane's box — issued at the end of C — is only needed by S1's second task round anyway.
+    static constexpr int NSW = PB;
     static constexpr int S1_TASKS = PB * EH * NQUAD;   // 800 / 720
     static constexpr int S2_TASKS = PB * 12 * NQUAD;   // 480 / 432 column-strip tasks
 };
@@ -77,7 +81,7 @@ struct Geom {
 };
 
 struct Params {
-    alignas(64) CUtensorMap noise_map;   // NOISE_TMA: 4-D view (W, H, D, B*12) of the noise tensor, box 40 x 20 x 1 x 12
+    alignas(64) CUtensorMap noise_map;   // NOISE_TMA: 4-D view (W, H, D, B*12) of the noise tensor, box 40 x 21 x 1 x 12
     const float *img;
     float *out;
     const float *noise;
@@ -802,7 +806,7 @@ static bool make_noise_map(Params &P)
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.D, (cuuint64_t)P.B * 12};
     const cuuint64_t strides[3] = {(cuuint64_t)P.W * 4, (cuuint64_t)P.H * P.W * 4, (cuuint64_t)P.D * P.H * P.W * 4};
-    const cuuint32_t box[4] = {Mode<NOISE_TMA>::EW, EH, 1, 12};
+    const cuuint32_t box[4] = {Mode<NOISE_TMA>::EW, Mode<NOISE_TMA>::BOX_ROWS, 1, 12};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(&P.noise_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(P.noise), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -813,7 +817,7 @@ template <int DELTA>
 static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
 {
     if (noise_mode == DGTTA_NOISE_TENSOR) {
-        constexpr int TMA_MAX_DELTA = CTAS_PER_SM == 1 ? 2 : 1;   // shared-memory budget
+        constexpr int TMA_MAX_DELTA = CTAS_PER_SM == 1 ? 3 : 1;   // shared-memory budget
         if (DELTA <= TMA_MAX_DELTA && make_noise_map(P))
             return launch<DELTA <= TMA_MAX_DELTA ? DELTA : 1, NOISE_TMA>(P, plan, workspace, stream);
         return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
@@ -835,7 +839,7 @@ void preload_mind_fast()
     touch_fast<1, DGTTA_NOISE_NONE>(); touch_fast<2, DGTTA_NOISE_NONE>(); touch_fast<3, DGTTA_NOISE_NONE>();
     touch_fast<1, DGTTA_NOISE_TENSOR>(); touch_fast<2, DGTTA_NOISE_TENSOR>(); touch_fast<3, DGTTA_NOISE_TENSOR>();
     touch_fast<1, fast::NOISE_TMA>();
-    if (fast::CTAS_PER_SM == 1) touch_fast<fast::CTAS_PER_SM == 1 ? 2 : 1, fast::NOISE_TMA>();
+    if (fast::CTAS_PER_SM == 1) { touch_fast<fast::CTAS_PER_SM == 1 ? 2 : 1, fast::NOISE_TMA>(); touch_fast<fast::CTAS_PER_SM == 1 ? 3 : 1, fast::NOISE_TMA>(); }
     DGTTA_TOUCH(fast::mind_fast_finalize);
 }
 
