@@ -81,6 +81,7 @@ struct Geom {
 };
 
 struct Params {
+    alignas(64) CUtensorMap img_map;     // NOISE_TMA: 3-D view (W, H, B*D) of the image, box 48 x tile rows x 1 (zero fill outside)
     alignas(64) CUtensorMap noise_map;   // NOISE_TMA: 4-D view (W, H, D, B*12) of the noise tensor, box 40 x 21 x 1 x 12
     const float *img;
     float *out;
@@ -150,6 +151,14 @@ __device__ __forceinline__ int opaque(int x)
     return x;
 }
 
+__device__ __forceinline__ void tma_load_3d(float *dst_smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 __device__ __forceinline__ float rcp_approx(float x)
 {
     float y;
@@ -189,7 +198,7 @@ __device__ __forceinline__ void st4p(float *p, u64 a, u64 b)
 // March one CTA over output planes [d0, d1) of patch (h0, w0) of sample b.
 template <int DELTA, int NOISE, bool FIX>
 __device__ __forceinline__ void process(const Params &P, float *smem, float (*red)[C_WARPS], uint64_t *full_bar,
-                                        uint64_t *empty_bar, int b, int h0, int w0, int d0, int d1, float lo, float hi,
+                                        uint64_t *empty_bar, uint64_t *img_bar, int b, int h0, int w0, int d0, int d1, float lo, float hi,
                                         float4 *stats)
 {
     using G = Geom<DELTA, NOISE>;
@@ -211,6 +220,21 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
     int loaded_hi;  // highest real plane resident in the ring
     auto load_until = [&](int need_hi) {
         need_hi = min(need_hi, D - 1);
+        if (TMA) {
+            // one box per image plane (48 columns from the 16-byte aligned w0-8, all tile rows; zeros outside the
+            // volume: S1 clamps the rows it reads and patches the W neighbours of the volume's first / last quad), all
+            // planes of the batch on one mbarrier.  Every batch arms the barrier, also with zero new planes.
+            if (tid == 0) {
+                const int np = max(need_hi - loaded_hi, 0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (np == 0) mbar_arrive(img_bar);
+                else mbar_expect_tx(img_bar, (unsigned)(np * G::TILE * sizeof(float)));
+                for (int p = loaded_hi + 1; p <= need_hi; ++p)
+                    tma_load_3d(tiles + (p % G::NSLOT) * G::TILE, &P.img_map, img_bar, w0 - CO - 4, h0 - R - DELTA, b * D + p);
+            }
+            loaded_hi = max(loaded_hi, need_hi);
+            return;
+        }
         if (loaded_hi >= need_hi) { cp_async_commit(); return; }
         const int t0 = opaque(tid);
         int cell_s[G::NCELL], cell_g[G::NCELL];
@@ -281,6 +305,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         if (tid == 0) {
 #pragma unroll
             for (int s = 0; s < NSW; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], C_WARPS); }
+            mbar_init(img_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
             for (int g = 0; g < NSW; ++g) issue_noise(g, z_begin + g);
@@ -294,7 +319,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
 
     for (int n = 0; n < nb; ++n) {
         const int zb = z_begin + n * PB;
-        cp_async_wait_all();
+        if (!TMA) cp_async_wait_all();
         __syncthreads();   // tiles of this batch visible; every thread finished C of the previous batch
         if (!FIX && n > 0 && warp == 0) {
             // statistics of the previous batch (warp partials were parked in `red` before the barrier)
@@ -320,15 +345,36 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
             const float *tm = tiles + (clampi(zc - DELTA, 0, D - 1) % G::NSLOT) * G::TILE + toff;
             const float *tp = tiles + (clampi(zc + DELTA, 0, D - 1) % G::NSLOT) * G::TILE + toff;
             u64 nbv[6][2];   // D-, D+, H-, H+, W-, W+ as (k0,k1),(k2,k3)
+            const int gw0 = w0 - CO + 4 * q;
+            int hm_off = -DELTA * TWD, hp_off = DELTA * TWD;
+            if (TMA) {
+                // image tiles arrive by TMA with zeros outside the volume: read the clamped row instead (replicate
+                // padding, mind.py:137); tile row i is h = h0 - R - DELTA + i
+                mbar_wait(img_bar, (unsigned)n & 1u);
+                const int row_lo = max(0, R + DELTA - h0), row_hi = min(G::TR - 1, H - 1 - h0 + R + DELTA);
+                hm_off = (max(rc, row_lo) - (rc + DELTA)) * TWD;
+                hp_off = (min(rc + 2 * DELTA, row_hi) - (rc + DELTA)) * TWD;
+            }
             ld4p(tm, nbv[NB_DM][0], nbv[NB_DM][1]);
             ld4p(tp, nbv[NB_DP][0], nbv[NB_DP][1]);
-            ld4p(tc - DELTA * TWD, nbv[NB_HM][0], nbv[NB_HM][1]);
-            ld4p(tc + DELTA * TWD, nbv[NB_HP][0], nbv[NB_HP][1]);
+            ld4p(tc + hm_off, nbv[NB_HM][0], nbv[NB_HM][1]);
+            ld4p(tc + hp_off, nbv[NB_HP][0], nbv[NB_HP][1]);
             float wr[12];      // centre row, positions -4 .. 7 relative to the quad
             ld4(tc - 4, &wr[0]); ld4(tc, &wr[4]); ld4(tc + 4, &wr[8]);
             float wm[4], wp[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { wm[k] = wr[4 + k - DELTA]; wp[k] = wr[4 + k + DELTA]; }
+            if (TMA) {
+                // same for the W neighbours of the volume's first and last quad (W % 4 == 0: quads are aligned)
+                if (gw0 == 0) {
+#pragma unroll
+                    for (int k = 0; k < DELTA; ++k) wm[k] = wr[4];
+                }
+                if (gw0 + 4 == W) {
+#pragma unroll
+                    for (int k = 4 - DELTA; k < 4; ++k) wp[k] = wr[7];
+                }
+            }
             if (!TMA && w0 == 0 && q == 0) {
                 // columns w < 0 take E of w = 0: only the W+ neighbour (I at w = delta) differs from the clamped loads
 #pragma unroll
@@ -351,7 +397,6 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                     for (int j = 0; j < 2; ++j) nbv[a][j] = fmul2(fmul2(nbv[a][j], SA), SC);
             }
             float *wsp = ws + slot_of(pz) * WS_PLANE + r * WSP + 4 * q;
-            const int gw0 = w0 - CO + 4 * q;
             if (TMA) {
                 // The task owns its quad only if row and quad lie inside the volume (W % 4 == 0: a quad is in or out as a
                 // whole); halo positions outside replicate E^2 of the clamped position (mind.py:22) and are written by
@@ -633,6 +678,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         if (tid == 0) {
 #pragma unroll
             for (int s = 0; s < NSW; ++s) { mbar_inval(&full_bar[s]); mbar_inval(&empty_bar[s]); }
+            mbar_inval(img_bar);
         }
     }
 }
@@ -655,9 +701,10 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const 
     __shared__ float red[3][C_WARPS];
     __shared__ uint64_t full_bar[PB + 1];
     __shared__ uint64_t empty_bar[PB + 1];
+    __shared__ uint64_t img_bar;
     int b, h0, w0, d0, d1;
     decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
-    process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, b, h0, w0, d0, d1, 0.f, 0.f,
+    process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, &img_bar, b, h0, w0, d0, d1, 0.f, 0.f,
                                  P.stats + (size_t)blockIdx.x * P.nbatch);
 }
 
@@ -669,6 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_fix_kernel(co
     __shared__ float red[3][C_WARPS];
     __shared__ uint64_t full_bar[PB + 1];
     __shared__ uint64_t empty_bar[PB + 1];
+    __shared__ uint64_t img_bar;
     const int count = P.fix_hdr[0];
     const float lo = P.fix_lohi[0], hi = P.fix_lohi[1];
     for (int u = blockIdx.x; u < count; u += gridDim.x) {
@@ -678,7 +726,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_fix_kernel(co
         decode_cta(P, cta, b, h0, w0, d0, d1);
         // batch n of pass 1 emitted planes d0 + PB*n - 2R .. + PB-1 (clipped to the chunk)
         const int lo_d = max(d0, d0 + n * PB - 2 * R), hi_d = min(d1 - 1, d0 + n * PB - 2 * R + PB - 1);
-        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, full_bar, empty_bar, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
+        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, full_bar, empty_bar, &img_bar, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
         __syncthreads();
     }
 }
@@ -813,12 +861,28 @@ static bool make_noise_map(Params &P)
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D view (W, H, B*D) of the image; box = one plane of the CTA's tile (48 columns x tile rows), zero fill outside
+template <int DELTA>
+static bool make_img_map(Params &P)
+{
+    if (reinterpret_cast<uintptr_t>(P.img) & 15) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.B * P.D};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.W * 4, (cuuint64_t)P.H * P.W * 4};
+    const cuuint32_t box[3] = {Mode<NOISE_TMA>::TWD, Geom<DELTA, NOISE_TMA>::TR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(&P.img_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P.img), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int DELTA>
 static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
 {
     if (noise_mode == DGTTA_NOISE_TENSOR) {
         constexpr int TMA_MAX_DELTA = CTAS_PER_SM == 1 ? 3 : 1;   // shared-memory budget
-        if (DELTA <= TMA_MAX_DELTA && make_noise_map(P))
+        if (DELTA <= TMA_MAX_DELTA && make_noise_map(P) && make_img_map<DELTA <= TMA_MAX_DELTA ? DELTA : 1>(P))
             return launch<DELTA <= TMA_MAX_DELTA ? DELTA : 1, NOISE_TMA>(P, plan, workspace, stream);
         return launch<DELTA, DGTTA_NOISE_TENSOR>(P, plan, workspace, stream);
     }
@@ -870,6 +934,7 @@ int mind_fast_launch(const MindArgs &a, cudaStream_t stream)
     }
     fast::Params P;
     memset(&P.noise_map, 0, sizeof(P.noise_map));
+    memset(&P.img_map, 0, sizeof(P.img_map));
     P.img = a.img; P.out = a.out; P.noise = a.noise; P.in_scale = a.in_scale;
     P.stats = nullptr; P.fix_hdr = nullptr; P.fix_lohi = nullptr;
     P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W;
