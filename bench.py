@@ -81,6 +81,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.recording = False   # the thread is started (and NVML warmed: its first queries take milliseconds and hold
+        #                          driver locks that stall kernel launches) before the timed region; rows are kept only
+        #                          while `recording` is set
         self.nvml = self.handle = None
         try:
             import pynvml
@@ -113,11 +116,13 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 if self.handle is not None:
-                    self.rows.append(self.sample_nvml())
+                    row = self.sample_nvml()
+                    if self.recording:
+                        self.rows.append(row)
                 else:
                     out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
+                    if out and self.recording:
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
@@ -215,9 +220,19 @@ def run_ours(args, rank, world, local_rank):
     # per step (57 MB in + 679 MB noise + 679 MB out) is far larger than the 126 MB L2
     xs = [synth_volume(SHAPE, 2000 + 10 * rank + i).to(dev) for i in range(3)]
 
+    DEPTH = 4   # steps in flight: the host never runs more than DEPTH steps ahead of the GPU, which keeps the set of live
+    #             679 MB descriptors (and so the caching allocator's pool) the same in every pass; the GPU queue stays fed
+    inflight = []
+
     def step(i):
+        if len(inflight) >= DEPTH:
+            inflight.pop(0).synchronize()
         torch.manual_seed(i)  # same host draws as the reference arm for step i
-        return gin_mind_aug(xs[i % 3])   # the public drop-in call
+        y = gin_mind_aug(xs[i % 3])   # the public drop-in call
+        ev = torch.cuda.Event()
+        ev.record()
+        inflight.append(ev)
+        return y
 
     def sync_all():
         torch.cuda.synchronize()
@@ -225,6 +240,9 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("DGTTA_BENCH_NO_SAMPLER"):
+        sampler.start()
     for i in range(args.warmup):
         step(i)
     sync_all()
@@ -233,12 +251,12 @@ def run_ours(args, rank, world, local_rank):
     # blocks.  The first time that happens the caching allocator has to cudaMalloc them (milliseconds each, on the
     # host, inside the loop).  Rehearsing the same enqueue pattern once grows the pool to its steady-state size and
     # ramps the SM clocks; the timed region below then measures the transform, not the allocator.
+    out = None
     for i in range(min(args.steps, 32)):
-        step(args.warmup + i)
+        out = step(args.warmup + i)   # keeps the previous descriptor alive across the next call, exactly like the timed loop
+    del out
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("DGTTA_BENCH_NO_SAMPLER"):
-        sampler.start()
+    sampler.recording = True
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.lib().dgtta_launch_count()
     import gc
@@ -312,6 +330,7 @@ def run_ours(args, rank, world, local_rank):
     u1.record()
     sync_all()
     e2e_ms = u0.elapsed_time(u1)
+    sampler.recording = False
     sampler.stop_flag = True
 
     times = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -347,6 +366,7 @@ def run_ours(args, rank, world, local_rank):
                                "sigma=1 with the torch.randn edge noise regenerated by the library's Philox kernel) on 2x1x192x192x192 fp32 per GPU (BASELINE.json "
                                "configs[1] shape)",
                    "l2": "3 rotating input batches; per-step working set 1.4 GB >> 126 MB L2",
+                   "queue": "at most 4 steps in flight (host waits on the event of step i-4)",
                    "seeds": "torch.manual_seed(step) -> GIN kernel sizes/weights identical to the reference arm",
                    "parallelism": f"{world} independent replicas, one batch per GPU, no collective"},
         "e2e": {"value": vox_step * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
@@ -354,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "dg_tta_b200.host_pipeline.HostPipeline.submit (H2D / transform / D2H of consecutive steps overlapped)"},
         "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (counted inside the library)
-        "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1,noise=TMA-staged tensor> (+finalize, fix-up)",
+        "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1, noise and image tiles staged by TMA> (+finalize, fix-up)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic[0] if traffic else None,
                      "traffic_source": f"profiles/{traffic[1]} (ncu --set full, dram read+write bytes per launch)" if traffic else None,

@@ -81,6 +81,30 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_scratch = {}
+
+
+def scratch(device, tag, numel):
+    """A float32 work buffer of >= numel elements that persists between calls (keyed by device, current stream and
+    tag), for intermediates that never leave an operator: the 12-channel noise field of MIND is 679 MB at 2x192^3, and
+    re-allocating it per call makes the caching allocator's pool depth — and with it cudaMalloc stalls on the host —
+    depend on how far the host runs ahead of the GPU.  Reuse is ordered by the stream the buffer is keyed on.
+    release_scratch() drops the buffers."""
+    import torch
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = None
+        _scratch.pop(key, None)
+        buf = _scratch[key] = torch.empty(numel, device=device, dtype=torch.float32)
+    return buf[:numel]
+
+
+def release_scratch():
+    _scratch.clear()
+
+
 def require_cuda_f32(t, name):
     """Boundary contract: CUDA, float32; made contiguous by the caller."""
     import torch

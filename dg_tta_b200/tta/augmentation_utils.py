@@ -109,11 +109,13 @@ def gin_mind_aug(input):
     side = _SIDE_STREAMS.get(dev.index)
     if side is None:
         side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
-    side.wait_stream(main)                                    # generator/allocator ordering with earlier work
+    # persistent 12-channel noise buffer of this (device, stream): the fill below waits for everything already queued
+    # on `main` — in particular the previous call's MIND, its last reader — so reuse is ordered
+    noise = _lib.scratch(dev, "gin_mind_aug_noise", B * 12 * D * H * W).view(B, 12, D, H, W)
+    side.wait_stream(main)
     with torch.cuda.stream(side):
-        noise = randn_like_reference((B, 12, D, H, W), dev)   # == torch.randn(...), generated by our Philox kernel
+        randn_like_reference((B, 12, D, H, W), dev, out=noise)   # == torch.randn(...), generated by our Philox kernel
     from ..gin import gin_forward
     mixed, scale = gin_forward(input, kers, shifts, alphas, net.interm_channel, defer_scale=True)
     main.wait_stream(side)
-    noise.record_stream(main)
     return mind_ssc(mixed, noise=noise, in_scale=scale)

@@ -120,10 +120,13 @@ def test_full_size_properties(shape, delta):
 
 
 @pytest.mark.parametrize("shape,delta", [((1, 1, 64, 64, 64), 1), ((2, 1, 40, 36, 72), 2), ((1, 1, 21, 12, 8), 1),
-                                         ((1, 1, 50, 100, 132), 3), ((2, 1, 192, 192, 192), 1)])
+                                         ((1, 1, 50, 100, 132), 3), ((2, 1, 192, 192, 192), 1), ((2, 1, 1, 16, 4), 1),
+                                         ((1, 1, 3, 20, 36), 2), ((1, 1, 7, 33, 100), 1), ((4, 1, 9, 64, 32), 3),
+                                         ((1, 1, 128, 128, 128), 2)])
 def test_tma_staged_noise_is_bitwise_the_ldg_path(shape, delta, monkeypatch):
-    """W % 4 == 0 takes the TMA-staged noise path (box copies into the E^2 planes); DGTTA_MIND_NO_TMA forces the
-    LDG path.  Same arithmetic -> bit-identical descriptors; the small cases are also checked against the oracle."""
+    """W % 4 == 0 takes the TMA path (noise boxes into the E^2 planes, image tiles as zero-filled boxes with the
+    replicate padding applied on read); DGTTA_MIND_NO_TMA forces the LDG / cp.async path.  Same arithmetic ->
+    bit-identical descriptors; the small cases are also checked against the oracle."""
     from dg_tta_b200 import MIND3D
     from oracle import cform
     x = synth_volume(shape, 77 + delta).cuda()
