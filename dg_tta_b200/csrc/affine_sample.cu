@@ -187,8 +187,43 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const
     }
 }
 
+// Label crop of get_batch (dg_tta/tta/torch_utils.py:71-82): nearest-neighbour sampling of the one-hot label channels
+// (zeros outside), background channel prepended where no label is set, argmax over channels — in one pass, writing the
+// int64 label map directly instead of an L-channel float patch plus sum / cat / argmax passes.  Ties go to the lowest
+// index like torch.argmax; the background channel is index 0.
+__global__ void __launch_bounds__(SAMPLE_THREADS) affine_label_argmax_kernel(const __grid_constant__ SampleParams P, long long *out)
+{
+    __shared__ BlockCoords S;
+    const int ntw = (P.Wo + SBX - 1) / SBX;
+    const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
+    const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
+    block_setup(P, S, b, w0, h0, d);
+    const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
+    if (w >= P.Wo || h >= P.Ho) return;
+    const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
+    const Coords c = source_coords<DGTTA_PAD_ZEROS>(P, S);
+    const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
+    const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
+    long long label = 0;
+    if (ok) {
+        const float *src = P.in + (size_t)b * P.C * Vi + ((size_t)(int)rz * P.Hi + (int)ry) * P.Wi + (int)rx;
+        float sum = 0.f, best = -__int_as_float(0x7f800000);
+        int arg = 0;
+        for (int ch = 0; ch < P.C; ++ch) {
+            const float v = __ldg(src + (size_t)ch * Vi);
+            sum += v;
+            if (v > best) { best = v; arg = ch + 1; }
+        }
+        const float bg = sum < 1.0f ? 1.f : 0.f;     // get_argmaxed_segs: (segs.sum(1) < 1.0).float()
+        label = bg >= best ? 0 : arg;
+    }
+    // outside the volume every channel samples 0: sum = 0 < 1 -> background
+    out[(size_t)b * Vo + ((size_t)d * P.Ho + h) * P.Wo + w] = label;
+}
+
 void preload_sampler()
 {
+    DGTTA_TOUCH(affine_label_argmax_kernel);
     DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS>);
     DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER>);
     DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_NEAREST, DGTTA_PAD_ZEROS>);
@@ -261,4 +296,14 @@ extern "C" int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const fl
     if (padding == DGTTA_PAD_ZEROS) affine_sample_bwd_kernel<DGTTA_PAD_ZEROS><<<grid, block, 0, stream>>>(P);
     else affine_sample_bwd_kernel<DGTTA_PAD_BORDER><<<grid, block, 0, stream>>>(P);
     return check_launch("affine_sample_bwd_kernel");
+}
+
+extern "C" int dgtta_affine_label_argmax(const float *onehot_dev, const float *theta_dev, long long *out_dev, int B, int L,
+                                         int Di, int Hi, int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream_)
+{
+    int rc = sample_check(onehot_dev, theta_dev, out_dev, B, L, Di, Hi, Wi, Do, Ho, Wo);
+    if (rc) return rc;
+    SampleParams P{onehot_dev, theta_dev, nullptr, B, L, Di, Hi, Wi, Do, Ho, Wo};
+    affine_label_argmax_kernel<<<sample_grid(B, Do, Ho, Wo), dim3(SBX, SBY, 1), 0, (cudaStream_t)stream_>>>(P, out_dev);
+    return check_launch("affine_label_argmax_kernel");
 }

@@ -87,6 +87,25 @@ def affine_grid_sample(input, theta, out_size=None, mode="bilinear", padding_mod
     return _AffineSample.apply(input, theta, size, _INTERP[mode], _PAD[padding_mode])
 
 
+def affine_label_argmax(onehot, theta, out_size=None):
+    """get_argmaxed_segs(F.grid_sample(onehot, F.affine_grid(theta, ...), mode="nearest", padding_mode="zeros"))
+    (dg_tta/tta/torch_utils.py:71-82) in one kernel: [B,L,D,H,W] float32 one-hot labels -> [B,1,*out_size] int64
+    label map with 0 = background."""
+    _lib.require_cuda_f32(onehot, "onehot")
+    if onehot.dim() != 5:
+        raise ValueError("affine_label_argmax expects [B,L,D,H,W]")
+    B, L, Di, Hi, Wi = onehot.shape
+    size = tuple(int(v) for v in (out_size[-3:] if out_size is not None else onehot.shape[-3:]))
+    theta = _theta_on(onehot.device, theta, B)
+    x = onehot.contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, 1) + size, device=x.device, dtype=torch.int64)
+        rc = _lib.lib().dgtta_affine_label_argmax(x.data_ptr(), theta.data_ptr(), out.data_ptr(), B, L, Di, Hi, Wi,
+                                                  size[0], size[1], size[2], _lib.stream_ptr())
+        _lib.check(rc, "dgtta_affine_label_argmax")
+    return out
+
+
 _SIDE_STREAMS = {}
 
 

@@ -1,6 +1,7 @@
 """Patch sampling of the TTA loop — drop-in for `get_batch` / `get_argmaxed_segs` of
 dg_tta/tta/torch_utils.py:13-82.  The affine_grid + grid_sample pairs (:55-62 image, zeros padding;
-:71-73 labels, nearest) run in the fused sampler kernel (csrc/affine_sample.cu); the host draws
+:71-73 labels, nearest, fused with get_argmaxed_segs :79-82 into one label-map kernel) run in the sampler kernels
+(csrc/affine_sample.cu); the host draws
 (`2*rand(3)-1` per batch element, CPU generator, :39) keep the reference's order.
 
 Volumes may already live on the device: the reference re-uploads the whole volume on every call
@@ -8,7 +9,7 @@ Volumes may already live on the device: the reference re-uploads the whole volum
 """
 import torch
 
-from .augmentation_utils import affine_grid_sample
+from .augmentation_utils import affine_grid_sample, affine_label_argmax
 
 
 def get_argmaxed_segs(segs):
@@ -51,7 +52,6 @@ def get_batch(tensor_list, batch_idxs, patch_size, fixed_patch_idx=None, device=
             if data[1:].numel() == 0:
                 b_label.append(None)   # no GT label available for this sample
             else:
-                lbl_patch = affine_grid_sample(data[1:][None].contiguous(), theta, out_size, mode="nearest",
-                                               padding_mode="zeros")
-                b_label.append(get_argmaxed_segs(lbl_patch))
+                # nearest-mode crop of the one-hot channels + background + argmax (:71-82), fused: no L-channel patch
+                b_label.append(affine_label_argmax(data[1:][None], theta, out_size))
     return b_img, b_label

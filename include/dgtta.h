@@ -128,6 +128,13 @@ int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_dev, float *
 int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const float *theta_dev, float *grad_in_dev, int B,
                                   int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int padding,
                                   dgtta_stream_t stream);
+/* Label crop.  Replaces the nearest-mode F.grid_sample of the one-hot label channels plus get_argmaxed_segs
+ * (dg_tta/tta/torch_utils.py:71-73, 79-82): out[b,0,p] = 0 (background) where the labels sampled at p sum to < 1 or
+ * p maps outside the volume, else 1 + argmax_l onehot[b,l,nearest(p)] (lowest index on ties, like torch.argmax).
+ *   onehot_dev [B,L,Di,Hi,Wi] float32   theta_dev [B,3,4]   out_dev [B,1,Do,Ho,Wo] int64 */
+int dgtta_affine_label_argmax(const float *onehot_dev, const float *theta_dev, long long *out_dev, int B, int L, int Di,
+                              int Hi, int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream);
+
 
 #ifdef __cplusplus
 }

@@ -118,3 +118,21 @@ def test_get_batch_matches_reference_crops():
     assert (l_lbl[0].cpu().numpy() != g["lbl_l"]).mean() <= 0.002
     img_only, none_lbl = get_batch([sample[:1]], [0], patch, fixed_patch_idx="center", device="cuda")
     assert none_lbl[0] is None and tuple(img_only[0].shape) == (1, 1, *patch)
+
+
+def test_label_argmax_equals_the_unfused_chain():
+    """dgtta_affine_label_argmax == get_argmaxed_segs(nearest grid_sample of the one-hot channels) (torch_utils.py:71-82),
+    bit for bit: same coordinates, same tie rule; overlapping / empty / fractional label channels included."""
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, affine_label_argmax, get_rand_affine
+    from dg_tta_b200.tta.torch_utils import get_argmaxed_segs
+    g = torch.Generator().manual_seed(3)
+    lab = (torch.rand(2, 7, 20, 18, 22, generator=g) > 0.8).float()     # overlapping labels and unlabeled voxels
+    lab[:, 5] *= 0.5                                                     # a fractional channel: sum < 1 with a set label
+    lab = lab.cuda()
+    torch.manual_seed(4)
+    R, _ = get_rand_affine(2, strength=0.2)
+    for size in (None, (9, 30, 11)):
+        unfused = get_argmaxed_segs(affine_grid_sample(lab, R, size, mode="nearest", padding_mode="zeros"))
+        fused = affine_label_argmax(lab, R, size)
+        assert fused.dtype == torch.int64 and tuple(fused.shape) == tuple(unfused.shape)
+        assert torch.equal(fused, unfused)
