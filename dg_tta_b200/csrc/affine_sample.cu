@@ -127,27 +127,40 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if (q.off[k] < 0) { q.off[k] = 0; q.wgt[k] = 0.f; }
+    // channel loop: the eight corner offsets and weights stay in registers, only the two channel base pointers move
+    // (one 64-bit add each per trip); four channels per trip keep 32 independent gathers in flight
+    const float *cb = src;
+    float *db = dst;
     int ch = 0;
     for (; ch + 4 <= P.C; ch += 4) {
         float v[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[u][k] = __ldg(src + (size_t)(ch + u) * Vi + q.off[k]);
+            for (int k = 0; k < 8; ++k) v[u][k] = __ldg(cb + (size_t)u * Vi + q.off[k]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc = fmaf(v[u][k], q.wgt[k], acc);
-            __stcs(dst + (size_t)(ch + u) * Vo, acc);
+            __stcs(db + (size_t)u * Vo, acc);
         }
+        cb += 4 * Vi;
+        db += 4 * Vo;
     }
-    for (; ch < P.C; ++ch) {
-        const float *sp = src + (size_t)ch * Vi;
+    for (; ch + 1 < P.C; ++ch) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(sp + q.off[k]), q.wgt[k], acc);
-        __stcs(dst + (size_t)ch * Vo, acc);
+        for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(cb + q.off[k]), q.wgt[k], acc);
+        __stcs(db, acc);
+        cb += Vi;
+        db += Vo;
+    }
+    if (ch < P.C) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(cb + q.off[k]), q.wgt[k], acc);
+        __stcs(db, acc);
     }
 }
 
@@ -172,18 +185,22 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const
     for (; ch + 4 <= P.C; ch += 4) {
         float g[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = __ldg(go + (size_t)(ch + u) * Vo);
+        for (int u = 0; u < 4; ++u) g[u] = __ldg(go + (size_t)u * Vo);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (q.off[k] >= 0) atomicAdd(gi + (size_t)(ch + u) * Vi + q.off[k], g[u] * q.wgt[k]);
+                if (q.off[k] >= 0) atomicAdd(gi + (size_t)u * Vi + q.off[k], g[u] * q.wgt[k]);
+        go += 4 * Vo;
+        gi += 4 * Vi;
     }
     for (; ch < P.C; ++ch) {
-        const float g = __ldg(go + (size_t)ch * Vo);
+        const float g = __ldg(go);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (q.off[k] >= 0) atomicAdd(gi + (size_t)ch * Vi + q.off[k], g * q.wgt[k]);
+            if (q.off[k] >= 0) atomicAdd(gi + q.off[k], g * q.wgt[k]);
+        go += Vo;
+        gi += Vi;
     }
 }
 
