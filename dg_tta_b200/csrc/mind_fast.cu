@@ -566,6 +566,18 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                         win[a][0][ph] = oa;
                         win[a][1][ph] = ob;
                     }
+                    if (TMA) {
+                        // the plane's values are in registers: release the slot now, and let thread 0 refill it as soon as
+                        // the other warps have got this far too (the last plane's box then leaves ~half a plane step
+                        // earlier than at the end of C)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[slot_of(ph)]);
+                        if (tid == 0) {
+                            const int sl = slot_of(ph);
+                            mbar_wait(&empty_bar[sl], (fill_parity >> sl) & 1u);
+                            issue_noise(sl, z + NSW);
+                        }
+                    }
                     float o[3][4];
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -626,24 +638,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                                 if (valid(k)) __stcs(op + a * ch_stride + k, o[a][k]);
                     }
                     op += emit ? HW : 0;
-                    if (TMA) {
-                        // this warp is done with the plane: arrive on the slot's empty barrier.  Thread 0 (lowest issue
-                        // priority, so usually the last warp anyway) refills the slot with plane z + NSW one plane later,
-                        // when the other 15 warps have normally arrived already.
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[slot_of(ph)]);
-                        if (ph > 0 && tid == 0) {
-                            const int sl = slot_of(ph - 1);
-                            mbar_wait(&empty_bar[sl], (fill_parity >> sl) & 1u);
-                            issue_noise(sl, z - 1 + NSW);
-                        }
-                    }
                 }
-            }
-            if (TMA && tid == 0) {
-                const int sl = slot_of(PB - 1);
-                mbar_wait(&empty_bar[sl], (fill_parity >> sl) & 1u);
-                issue_noise(sl, zb + PB - 1 + NSW);
             }
             if (!FIX) {
                 st_sum = warp_sum(st_sum); st_min = warp_min(st_min); st_max = warp_max(st_max);
