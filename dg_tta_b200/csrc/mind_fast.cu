@@ -795,7 +795,11 @@ template <int DELTA, int NOISE>
 static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStream_t stream)
 {
     using G = Geom<DELTA, NOISE>;
-    static bool configured = false;
+    // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
+    static bool configured_on[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    bool &configured = configured_on[dev];
     if (!configured) {
         cudaFuncSetAttribute(mind_fast_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         cudaFuncSetAttribute(mind_fast_fix_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);

@@ -305,7 +305,11 @@ template <int R, int NOISE>
 static int mind_launch(const MindParams &P, int ntiles, cudaStream_t stream)
 {
     using G = MindGeom<R>;
-    static bool configured = false;
+    // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
+    static bool configured_on[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    bool &configured = configured_on[dev];
     if (!configured) {
         cudaFuncSetAttribute(mind_general_kernel<R, false, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         cudaFuncSetAttribute(mind_general_kernel<R, true, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
