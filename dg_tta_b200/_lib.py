@@ -33,6 +33,8 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dgtta_affine_sample_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
     "dgtta_affine_sample_bwd_input": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "dgtta_consistency_sums_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
+    "dgtta_consistency_sums_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "dgtta_affine_label_argmax": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
 }
 

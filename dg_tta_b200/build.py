@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libdgtta_sm100.so"
-SOURCES = ["api.cu", "mind_ssc.cu", "mind_fast.cu", "mind_general.cu", "gin.cu", "gin_fused.cu", "affine_sample.cu", "philox_normal.cu"]
+SOURCES = ["api.cu", "mind_ssc.cu", "mind_fast.cu", "mind_general.cu", "gin.cu", "gin_fused.cu", "affine_sample.cu", "philox_normal.cu", "consistency_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--shared",

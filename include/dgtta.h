@@ -136,6 +136,21 @@ int dgtta_affine_label_argmax(const float *onehot_dev, const float *theta_dev, l
                               int Hi, int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream);
 
 
+/* ---------------------------------------------------------------------------------------------
+ * Consistency-loss reductions of the TTA step.  Replace the elementwise chain of dg_tta/tta/tta.py:263-268
+ * (common-content mask, channel softmax of both branches) and the per-(sample, class) sums inside
+ * soft_dice_loss (dg_tta/tta/torch_utils.py:94-95):
+ *     sums[b,c,0] = sum_v 2 sm_a sm_b        sums[b,c,1] = sum_v (sm_a + sm_b)^2
+ * with sm_x = softmax_c(target_x) * [sum_c target_a > 0][sum_c target_b > 0].  The caller finishes
+ * dice = (sums0/V) / (0.5 sums1/V) and loss = 1 - mean(dice[:, 1:]) on the [B,C] scalars.
+ *   target_a_dev, target_b_dev [B,C,V] float32 (V = D*H*W)   sums_dev [B,C,2] float64 (overwritten)
+ * bwd: grad_a_dev [B,C,V] = d loss / d target_a for grad_sums_dev [B,C,2] float32 = d loss / d sums
+ * (the mask is piecewise constant: no gradient through it, as in torch).  C <= 128. */
+int dgtta_consistency_sums_fwd(const float *target_a_dev, const float *target_b_dev, double *sums_dev, int B, int C,
+                               long long V, dgtta_stream_t stream);
+int dgtta_consistency_sums_bwd(const float *target_a_dev, const float *target_b_dev, const float *grad_sums_dev,
+                               float *grad_a_dev, int B, int C, long long V, dgtta_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,53 @@
+"""Fused consistency loss (dg_tta_b200.tta.torch_utils.consistency_dice_loss) against the reference's op chain
+(dg_tta/tta/tta.py:263-269 + torch_utils.py:90-104) written out in torch: loss value and gradient w.r.t. target_a."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_loss(target_a, target_b, start_class=1):
+    mask = (target_a.sum(1, keepdim=True) > 0.0).float() * (target_b.sum(1, keepdim=True) > 0.0).float()
+    sm_a = target_a.softmax(1) * mask
+    sm_b = target_b.softmax(1) * mask
+    B, _, D, H, W = sm_a.shape
+    nominator = (2.0 * sm_a * sm_b).reshape(B, -1, D * H * W).mean(2)
+    denominator = 0.5 * ((sm_a + sm_b) ** 2).reshape(B, -1, D * H * W).mean(2)
+    dice = (nominator * 0.0) + 1.0 if denominator.sum() == 0.0 else nominator / denominator
+    return 1 - dice[:, start_class:].mean()
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 12, 14, 16), (1, 14, 20, 24, 28), (2, 17, 9, 10, 11), (1, 40, 6, 7, 8),
+                                   (2, 14, 64, 64, 64)])
+def test_loss_and_gradient_match_the_reference_chain(shape):
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss
+    g = torch.Generator(device="cuda").manual_seed(shape[1])
+    a = torch.randn(shape, device="cuda", generator=g) * 2 + 0.3
+    b = torch.randn(shape, device="cuda", generator=g) * 2 + 0.3
+    a[:, :, :3] = 0.0                      # warped-in zeros: outside the common content (sum == 0 -> masked)
+    b[:, :, :, -2:] = 0.0
+    a1 = a.clone().requires_grad_(True)
+    a2 = a.clone().requires_grad_(True)
+    ref = reference_loss(a1, b)
+    got = consistency_dice_loss(a2, b)
+    assert abs(float(got) - float(ref)) <= 1e-5
+    ref.backward()
+    got.backward()
+    scale = float(a1.grad.abs().max())
+    assert scale > 0
+    assert float((a2.grad - a1.grad).abs().max()) <= 2e-5 * scale + 1e-10
+    assert float(a2.grad[:, :, :3].abs().max()) == 0.0          # masked voxels get no gradient
+
+
+def test_gradient_for_both_branches_and_empty_overlap():
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss
+    a = torch.randn(1, 6, 8, 8, 8, device="cuda").requires_grad_(True)
+    b = torch.randn(1, 6, 8, 8, 8, device="cuda").requires_grad_(True)
+    a_ref, b_ref = a.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    consistency_dice_loss(a, b).backward()
+    reference_loss(a_ref, b_ref).backward()
+    for x, y in ((a, a_ref), (b, b_ref)):
+        assert float((x.grad - y.grad).abs().max()) <= 2e-5 * float(y.grad.abs().max()) + 1e-10
+    # no common content at all: denominator.sum() == 0 -> dice = 1 -> loss = 0 (torch_utils.py:97-98)
+    z = torch.zeros(1, 6, 4, 4, 4, device="cuda")
+    assert float(consistency_dice_loss(z, z)) == 0.0

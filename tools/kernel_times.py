@@ -75,6 +75,22 @@ def main():
     go = torch.randn_like(out)
     med, best = timeit(lambda: torch.autograd.grad(out, lg, go, retain_graph=True))
     res["sample_logits_bwd_2x14x128"] = dict(ms=med, best=best, gbs=lg.numel() * 12 / med / 1e6)
+    # consistency loss: fused sums (+ gradient) vs the reference's elementwise chain, on the warped logits' shape
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss
+    ta = torch.randn(2, 14, 128, 128, 128, device="cuda", requires_grad=True)
+    tb = torch.randn(2, 14, 128, 128, 128, device="cuda")
+
+    def chain():
+        m = (ta.sum(1, keepdim=True) > 0.0).float() * (tb.sum(1, keepdim=True) > 0.0).float()
+        sa, sb = ta.softmax(1) * m, tb.softmax(1) * m
+        n = (2.0 * sa * sb).reshape(2, -1, 128 ** 3).mean(2)
+        d = 0.5 * ((sa + sb) ** 2).reshape(2, -1, 128 ** 3).mean(2)
+        return 1 - (n / d)[:, 1:].mean()
+
+    for name, fn in (("closs_fused_fwd_bwd_2x14x128", lambda: torch.autograd.grad(consistency_dice_loss(ta, tb), ta)),
+                     ("closs_torch_fwd_bwd_2x14x128", lambda: torch.autograd.grad(chain(), ta))):
+        med, best = timeit(fn)
+        res[name] = dict(ms=med, best=best, gbs=ta.numel() * 4 * 5 / med / 1e6)   # read a,b twice + write grad: 5 passes
     # torch eager comparison for the sampler
     import torch.nn.functional as F
     Rd = R.cuda()

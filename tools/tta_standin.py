@@ -91,10 +91,14 @@ def tta_inner_step(model, volumes, patch_size, batch_size, optimized_idx, transf
     imgs = torch.cat(imgs, dim=0)
     target_a = calc_branch(model, imgs, optimized_idx, True, transforms)     # have_grad_in = branch_a
     target_b = calc_branch(model, imgs, optimized_idx, False, transforms)
-    mask = (target_a.sum(1, keepdim=True) > 0.0).float() * (target_b.sum(1, keepdim=True) > 0.0).float()
-    sm_a = target_a.softmax(1) * mask
-    sm_b = target_b.softmax(1) * mask
-    loss = 1 - soft_dice_loss(sm_a, sm_b)[:, 1:].mean()                      # START_CLASS = 1
+    fused = getattr(transforms, "consistency_loss", None)
+    if fused is not None:                                                    # drop-in: mask + softmaxes + Dice sums in one pass
+        loss = fused(target_a, target_b, 1)
+    else:                                                                    # the reference's chain, tta.py:263-269
+        mask = (target_a.sum(1, keepdim=True) > 0.0).float() * (target_b.sum(1, keepdim=True) > 0.0).float()
+        sm_a = target_a.softmax(1) * mask
+        sm_b = target_b.softmax(1) * mask
+        loss = 1 - soft_dice_loss(sm_a, sm_b)[:, 1:].mean()                  # START_CLASS = 1
     (loss / accum).backward()
     return loss.detach()
 
@@ -110,6 +114,7 @@ class DropInTransforms:
         self.gin_hook, self.mind_hook = gin.gin_hook, mind.mind_hook
         self.get_rand_affine, self.get_batch = au.get_rand_affine, tu.get_batch
         self._sample = au.affine_grid_sample
+        self.consistency_loss = tu.consistency_dice_loss
 
     def warp(self, x, theta, padding):
         return self._sample(x, theta, padding_mode=padding)
