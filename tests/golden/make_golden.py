@@ -305,9 +305,31 @@ def gen_affine():
          seed_large=52, patch_large=np.array([16, 10, 20]), img_l=l_img[0], lbl_l=l_lbl[0])
 
 
+def gen_consistency():
+    # consistency loss of the TTA step: dg_tta/tta/tta.py:263-269 written out around the reference's own
+    # soft_dice_loss (dg_tta/tta/torch_utils.py:90-104); loss and d loss / d target_a
+    g = torch.Generator().manual_seed(77)
+    ta = (torch.randn(2, 6, 10, 12, 14, generator=g) * 2 + 0.3)
+    tb = (torch.randn(2, 6, 10, 12, 14, generator=g) * 2 + 0.3)
+    ta[:, :, :2] = 0.0          # zeros warped in from outside the volume -> outside the common-content mask
+    tb[:, :, :, -3:] = 0.0
+    ta.requires_grad_(True)
+    mask = (ta.sum(1, keepdim=True) > 0.0).float() * (tb.sum(1, keepdim=True) > 0.0).float()
+    sm_a = ta.softmax(1) * mask
+    sm_b = tb.softmax(1) * mask
+    loss = 1 - ref_tu.soft_dice_loss(sm_a, sm_b)[:, 1:].mean()
+    loss.backward()
+    save("consistency", target_a=ta.detach(), target_b=tb, loss=loss.detach(), grad_a=ta.grad)
+    # label crop: get_argmaxed_segs (torch_utils.py:79-82) on overlapping / empty / fractional channels
+    seg = (torch.rand(1, 5, 6, 7, 8, generator=g) > 0.7).float()
+    seg[:, 3] *= 0.5
+    save("argmaxed_segs", segs=seg, out=ref_tu.get_argmaxed_segs(seg))
+
+
 if __name__ == "__main__":
     gen_mind()
     gen_gin()
     gen_affine()
+    gen_consistency()
     total = sum(p.stat().st_size for p in OUT.glob("*.npz"))
     print(f"total fixture bytes: {total}")

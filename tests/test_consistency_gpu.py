@@ -1,9 +1,33 @@
 """Fused consistency loss (dg_tta_b200.tta.torch_utils.consistency_dice_loss) against the reference's op chain
 (dg_tta/tta/tta.py:263-269 + torch_utils.py:90-104) written out in torch: loss value and gradient w.r.t. target_a."""
+import numpy as np
 import pytest
 import torch
 
+from conftest import load_golden
+from gpu_util import cuda
+
 pytestmark = pytest.mark.gpu
+
+
+def test_golden_from_the_reference_soft_dice_loss():
+    """fixture generated with the reference's own soft_dice_loss (tests/golden/make_golden.py::gen_consistency)"""
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss
+    g = load_golden("consistency")
+    ta = cuda(g["target_a"]).requires_grad_(True)
+    loss = consistency_dice_loss(ta, cuda(g["target_b"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5
+    loss.backward()
+    assert np.abs(ta.grad.cpu().numpy() - g["grad_a"]).max() <= 2e-5 * np.abs(g["grad_a"]).max()
+
+
+def test_label_argmax_golden_identity_crop():
+    """get_argmaxed_segs fixture from the reference; an identity crop must reproduce it exactly"""
+    from dg_tta_b200.tta.augmentation_utils import affine_label_argmax
+    g = load_golden("argmaxed_segs")
+    theta = torch.eye(3, 4)[None]
+    out = affine_label_argmax(cuda(g["segs"]), theta)
+    assert np.array_equal(out.cpu().numpy(), g["out"])
 
 
 def reference_loss(target_a, target_b, start_class=1):
@@ -30,7 +54,7 @@ def test_loss_and_gradient_match_the_reference_chain(shape):
     a2 = a.clone().requires_grad_(True)
     ref = reference_loss(a1, b)
     got = consistency_dice_loss(a2, b)
-    assert abs(float(got) - float(ref)) <= 1e-5
+    assert abs(got.item() - ref.item()) <= 1e-5
     ref.backward()
     got.backward()
     scale = float(a1.grad.abs().max())
