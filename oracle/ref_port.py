@@ -104,3 +104,21 @@ def tta_view_warp(src, theta, identity_grid, padding_mode):
 def gin_mind(x, kers, shifts, alphas, noise=None, **mind_kw):
     """dg_tta/tta/augmentation_utils.py:173-174."""
     return mind_ssc(gin(x, kers, shifts, alphas), noise=noise, **mind_kw)
+
+
+def argmaxed_segs(segs):
+    """dg_tta/tta/torch_utils.py:79-82 (get_argmaxed_segs): background channel where no label is set, then argmax."""
+    with_bg = torch.cat([(segs.sum(1, keepdim=True) < 1.0).float(), segs], dim=1)
+    return with_bg.argmax(1, keepdim=True)
+
+
+def consistency_loss(target_a, target_b, start_class=1):
+    """dg_tta/tta/tta.py:263-269 with soft_dice_loss of dg_tta/tta/torch_utils.py:90-104 written out."""
+    mask = (target_a.sum(1, keepdim=True) > 0.0).float() * (target_b.sum(1, keepdim=True) > 0.0).float()
+    sm_a = target_a.softmax(1) * mask
+    sm_b = target_b.softmax(1) * mask
+    B, _, D, H, W = sm_a.shape
+    nominator = (2.0 * sm_a * sm_b).reshape(B, -1, D * H * W).mean(2)
+    denominator = 0.5 * ((sm_a + sm_b) ** 2).reshape(B, -1, D * H * W).mean(2)
+    dice = (nominator * 0.0) + 1.0 if denominator.sum() == 0.0 else nominator / denominator
+    return 1 - dice[:, start_class:].mean()

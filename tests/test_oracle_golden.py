@@ -155,3 +155,22 @@ def test_affine_general_modes():
     for pad in ("zeros", "border"):
         gi = cform.affine_sample_bwd_input(g["grad_out"], g["theta"], g["src"].shape, padding_mode=pad)
         assert np.abs(gi - g[f"grad_src_{pad}"]).max() <= 5e-5
+
+
+def test_consistency_loss_port_matches_reference_fixture():
+    """oracle/ref_port.consistency_loss against the fixture produced with the reference's soft_dice_loss"""
+    import torch
+    from oracle import ref_port
+    g = load_golden("consistency")
+    ta = torch.from_numpy(g["target_a"]).requires_grad_(True)
+    loss = ref_port.consistency_loss(ta, torch.from_numpy(g["target_b"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6
+    loss.backward()
+    assert np.abs(ta.grad.numpy() - g["grad_a"]).max() <= 1e-7
+
+
+def test_argmaxed_segs_port_matches_reference_fixture():
+    import torch
+    from oracle import ref_port
+    g = load_golden("argmaxed_segs")
+    assert np.array_equal(ref_port.argmaxed_segs(torch.from_numpy(g["segs"])).numpy(), g["out"])
