@@ -9,7 +9,7 @@ The deformable branch of the reference (augmentation_utils.py:8-153) is dead cod
 import torch
 
 from .. import _lib
-from ..gin import GINGroupConv, _GIN_CFG
+from ..gin import default_gin
 from ..mind import mind_ssc, randn_like_reference
 
 _INTERP = {"bilinear": 0, "nearest": 1}
@@ -120,7 +120,7 @@ def gin_mind_aug(input):
     _lib.require_cuda_f32(input, "input")
     if input.dim() != 5 or input.shape[1] != 1:
         raise ValueError(f"gin_mind_aug expects [B,1,D,H,W], got {tuple(input.shape)}")
-    net = GINGroupConv(dict(_GIN_CFG))
+    net = default_gin()
     alphas, kers, shifts = net.draw(input)                    # host draws + device rand(B), reference order
     B, _, D, H, W = input.shape
     dev = input.device

@@ -63,6 +63,26 @@ def main():
             seed += 1
         med, best = timeit(lambda: gin_forward(x, kers, shifts, alphas, 2))
         res["gin_k" + "".join(map(str, want))] = dict(ms=med, best=best, gvox_s=x.numel() / med / 1e6, gbs=x.numel() * 8 / med / 1e6)
+    # gin_aug over seeds 0..15 (all 16 draws of the four kernel sizes occur with equal probability)
+    from dg_tta_b200.gin import gin_aug
+    per_seed = []
+    for seed in range(16):
+        def run(seed=seed):
+            torch.manual_seed(seed)
+            return gin_aug(x)
+        med, _ = timeit(run, iters=5, warm=2)
+        per_seed.append(med)
+    res["gin_aug_seeds0_15_2x192"] = dict(ms=sum(per_seed) / 16, best=min(per_seed), worst=max(per_seed),
+                                          gvox_s=x.numel() / (sum(per_seed) / 16) / 1e6)
+    # GIN -> MIND on the MultiRes volume / patch shapes
+    from dg_tta_b200.tta.augmentation_utils import gin_mind_aug
+    for dhw in [(231, 228, 242), (116, 114, 121), (58, 57, 60), (38, 38, 40), (56, 56, 64), (28, 28, 32), (19, 19, 21)]:
+        xm = synth_volume((2, 1) + dhw, 4).cuda()
+        def run(xm=xm):
+            torch.manual_seed(1)
+            return gin_mind_aug(xm)
+        med, best = timeit(run, iters=5, warm=2)
+        res["gin_mind_aug_2x%dx%dx%d" % dhw] = dict(ms=med, best=best, gvox_s=xm.numel() / med / 1e6)
     torch.manual_seed(0)
     R, Ri = get_rand_affine(2)
     img = synth_volume((2, 1, 128, 128, 128), 3).cuda()
