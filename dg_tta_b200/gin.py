@@ -40,10 +40,9 @@ class GradlessGCReplayNonlinBlock(nn.Module):
 
     def draw(self, nb):
         """The three host draws of gin.py:65-66,94-103 in reference order."""
-        idx_k = torch.randint(high=len(self.scale_pool), size=(1,))
-        k = self.scale_pool[idx_k[0]]
-        ker = torch.randn([self.out_channel * nb, self.in_channel, k, k, k], requires_grad=self.requires_grad)
-        shift = torch.randn([self.out_channel * nb, 1, 1, 1], requires_grad=self.requires_grad) * 1.0
+        k = self.scale_pool[int(torch.randint(high=len(self.scale_pool), size=(1,)))]
+        ker = torch.randn([self.out_channel * nb, self.in_channel, k, k, k])
+        shift = torch.randn([self.out_channel * nb, 1, 1, 1])   # (the reference's "* 1.0" changes no value)
         return k, ker, shift
 
     def forward(self, x_in, requires_grad=False):
@@ -81,13 +80,10 @@ def gin_forward(x, kers, shifts, alphas, interm_channels, defer_scale=False):
     B, C, D, H, W = x.shape
     n_layer = len(kers)
     ksizes = [int(k.shape[-1]) for k in kers]
-    flat = []
-    for ker, shift in zip(kers, shifts):
-        flat.append(ker.detach().reshape(-1).to(torch.float32))
-        flat.append(shift.detach().reshape(-1).to(torch.float32))
-    params = torch.cat(flat).contiguous()
-    if params.is_cuda:
+    if any(t.is_cuda for t in kers) or any(t.is_cuda for t in shifts):
         raise TypeError("GIN weights are host draws (gin.py:94-103); pass CPU tensors")
+    with torch.no_grad():
+        params = torch.cat([t.reshape(-1) for pair in zip(kers, shifts) for t in pair]).to(torch.float32)
     ks = (ctypes.c_int * n_layer)(*ksizes)
     alphas = alphas.reshape(-1).contiguous()
     if alphas.numel() != B:
