@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const
     }
 }
 
-// adjoint of the trilinear forward: scatter grad_out into grad_in (pre-zeroed) with red.global.add
+// adjoint of the trilinear forward: scatter grad_out into grad_in (pre-zeroed) with red.global.add.
+// A warp is 32 consecutive output voxels along w; under the near-identity affines of the TTA loop lane i's x0+1 corner
+// is lane i+1's x0 corner, so that half of each lane's contributions is handed to the neighbour by shuffle and added
+// there first: ~4.1 instead of 8 global reductions per voxel and channel (the scatter is bound by L2 atomics).
 template <int PAD>
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const __grid_constant__ SampleParams P)
 {
@@ -174,31 +177,48 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const
     const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
     const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
     block_setup(P, S, b, w0, h0, d);
-    const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
-    if (w >= P.Wo || h >= P.Ho) return;
+    const int lane = threadIdx.x;   // blockDim.x == 32: a warp is one row of the block
+    const int w = w0 + lane, h = h0 + threadIdx.y;
+    const bool active = w < P.Wo && h < P.Ho;   // inactive lanes stay for the shuffles and contribute nothing
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
     const Coords c = source_coords<PAD>(P, S);
-    const Corners q = trilinear_corners(P, c);
-    const float *go = P.in + (size_t)b * P.C * Vo + ((size_t)d * P.Ho + h) * P.Wo + w;
+    Corners q = trilinear_corners(P, c);
+    if (!active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q.off[k] = -1;
+    }
+    // pair p = (dy, dz): corners 2p (x0) and 2p+1 (x0+1)
+    bool give[4], take[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int next_x0 = __shfl_down_sync(0xffffffffu, q.off[2 * p], 1);
+        give[p] = lane < 31 && q.off[2 * p + 1] >= 0 && next_x0 == q.off[2 * p + 1];
+        take[p] = __shfl_up_sync(0xffffffffu, (int)give[p], 1) != 0 && lane > 0;
+    }
+    const float *go = P.in + (size_t)b * P.C * Vo + ((size_t)d * P.Ho + min(h, P.Ho - 1)) * P.Wo + min(w, P.Wo - 1);
     float *gi = P.out + (size_t)b * P.C * Vi;
+    auto scatter = [&](float g, float *base) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float v1 = g * q.wgt[2 * p + 1];
+            const float from_left = __shfl_up_sync(0xffffffffu, v1, 1);
+            const float v0 = g * q.wgt[2 * p] + (take[p] ? from_left : 0.f);
+            if (q.off[2 * p] >= 0) atomicAdd(base + q.off[2 * p], v0);
+            if (q.off[2 * p + 1] >= 0 && !give[p]) atomicAdd(base + q.off[2 * p + 1], v1);
+        }
+    };
     int ch = 0;
     for (; ch + 4 <= P.C; ch += 4) {
         float g[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = __ldg(go + (size_t)u * Vo);
+        for (int u = 0; u < 4; ++u) g[u] = active ? __ldg(go + (size_t)u * Vo) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (q.off[k] >= 0) atomicAdd(gi + (size_t)u * Vi + q.off[k], g[u] * q.wgt[k]);
+        for (int u = 0; u < 4; ++u) scatter(g[u], gi + (size_t)u * Vi);
         go += 4 * Vo;
         gi += 4 * Vi;
     }
     for (; ch < P.C; ++ch) {
-        const float g = __ldg(go);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (q.off[k] >= 0) atomicAdd(gi + q.off[k], g * q.wgt[k]);
+        scatter(active ? __ldg(go) : 0.f, gi);
         go += Vo;
         gi += Vi;
     }
