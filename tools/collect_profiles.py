@@ -38,7 +38,7 @@ if ll.exists():
     shutil.copy(ll, dst / ll.name)
 
 for rep, vox in ((f"{tag}_mind_noise", 2 * 192 ** 3), (f"{tag}_mind_clean", 2 * 192 ** 3), (f"{tag}_gin3333", 192 ** 3),
-                 (f"{tag}_sampler", 2 * 128 ** 3), (f"{tag}_philox", 2 * 12 * 192 ** 3)):
+                 (f"{tag}_sampler", 2 * 128 ** 3), (f"{tag}_philox", 2 * 12 * 192 ** 3), (f"{tag}_closs", 2 * 128 ** 3)):
     path = src / f"{rep}.ncu-rep"
     if not path.exists():
         continue

@@ -17,6 +17,8 @@ ncu --set full --clock-control none --import-source on -k regex:"affine_sample" 
     python tools/prof_mind.py sampler > gpurun_out/${tag}_ncu_sampler.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"normal_fill_kernel" -s 1 -c 1 -o gpurun_out/${tag}_philox \
     python tools/prof_mind.py philox > gpurun_out/${tag}_ncu_philox.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"sums_kernel|grad_kernel" -s 2 -c 2 -o gpurun_out/${tag}_closs \
+    python tools/prof_closs.py > gpurun_out/${tag}_ncu_closs.log 2>&1
 # 3. the numbers themselves (never taken under a profiler)
 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err
