@@ -3,17 +3,26 @@
 //
 // One CTA (512 threads, one per SM) owns a 16 x 32 patch of the H-W plane and marches along D in
 // batches of PB = 4 planes.  All arithmetic is packed fp32x2 (FFMA2/FMUL2/FADD2).  Per batch:
-//   T  cp.async ring of raw image planes: tile[slot][20+2d][44] holds I at clamped coordinates
-//      (replicate padding of mind.py:137 is folded into the addresses); only PB new planes per batch.
-//   S1 720 tasks (plane, halo row, 4 columns): the task loads the 6-neighbourhood of its 4 positions
-//      (LDS.128) and writes the 12 squared edge channels -> ws[plane][c][row][col] (STS.128).
-//   S2 432 tasks (plane, channel, 4-column strip): H smoothing with a sliding 5-row register window, in
-//      place (LDS.128 / STS.128), exactly one task per thread.
+//   T  ring of raw image planes in shared memory, only PB new planes per batch.
+//      LDG modes : cp.async, tile[slot][20+2d][44] holds I at clamped coordinates (the replicate padding of
+//                  mind.py:137 is folded into the addresses).
+//      TMA mode  : one 48-column box per plane (UTMALDG.3D, zeros outside the volume); S1 clamps the rows it
+//                  reads and patches the W neighbours of the volume's first / last quad instead.
+//   S1 tasks (plane, halo row, 4 columns) — 720 (36-column tile) or 800 (TMA mode, aligned 40-column tile): the
+//      task loads the 6-neighbourhood of its 4 positions (LDS.128), adds the noise and writes the 12 squared edge
+//      channels -> ws[plane][c][row][col] (STS.128).  Noise: LDG modes read it from global memory (L2-prefetched);
+//      TMA mode finds it already in ws — one 40 x 21 x 12-channel box per plane (UTMALDG.4D) lands where E^2
+//      goes and is squared in place; the four ws planes are a ring refilled (plane z+4) as soon as stage C has the
+//      plane's values in registers (full / empty mbarriers).
+//   S2 tasks (plane, channel, 4-column strip), one per thread: H smoothing with a sliding 5-row register window,
+//      in place (LDS.128 / STS.128); conflict-free in both layouts (channel pitch 185 resp. 210 16-byte chunks).
 //   C  warp = patch row; thread = (4 consecutive voxels) x (3 channels); lanes = 8 column groups x 4
-//      channel groups.  Per plane: 2 LDS.128 per channel give 4 W-smoothed values; the D smoothing runs
+//      channel groups.  Per plane: the 8 values of the thread's W windows per channel (2 LDS.128, or
+//      LDS.64 + LDS.128 + LDS.64 in the 40-column tile) give 4 W-smoothed values; the D smoothing runs
 //      on a 4-slot register window (slots are compile-time because PB == taps - 1); min / mean over the 12
 //      channels by two xor-shuffles; exp; one STG.128 per channel (full 128-byte lines per warp).
-// Three __syncthreads per 4 planes; the only HBM traffic is 4 B/voxel in (+halo via L2) and 48 B/voxel out.
+// Three __syncthreads per 4 planes; HBM traffic is 4 B/voxel in (+halo via L2), 48 B/voxel of noise when it is
+// streamed in (x1.6 box over-read, mostly L2 hits) and 48 B/voxel out.
 //
 // Global clamp (mind.py:158-160): pass 1 assumes it inactive and records {sum v, min positive v, max v}
 // per (CTA, batch).  mind_fast_finalize reduces them to mean_all(v) and lists the (CTA, batch) units whose
