@@ -146,3 +146,28 @@ def affine_sample_bwd_input(grad_out, theta, in_size, padding_mode="zeros", prec
     fn(_ptr(grad_out), _ptr(theta), _ptr(gin_, ctypes.c_float if precision == "f32" else ctypes.c_double),
        B, C, Di, Hi, Wi, Do, Ho, Wo, _PADS[padding_mode])
     return gin_
+
+
+def consistency_loss(target_a, target_b, start_class=1, precision="f32", with_grad=True):
+    """Loss of tta.py:263-269 (+ soft_dice_loss, torch_utils.py:90-104) and its gradient w.r.t. target_a."""
+    ta, tb = _f32(target_a), _f32(target_b)
+    B, C = ta.shape[:2]
+    V = int(np.prod(ta.shape[2:]))
+    dt, ct = (np.float32, ctypes.c_float) if precision == "f32" else (np.float64, ctypes.c_double)
+    grad = np.empty(ta.shape, dt) if with_grad else None
+    fn = getattr(lib(), f"oracle_consistency_loss_{precision}")
+    fn.restype = ct
+    loss = fn(_ptr(ta), _ptr(tb), _ptr(grad, ct) if with_grad else None, B, C, ctypes.c_long(V), int(start_class))
+    return (float(loss), grad) if with_grad else float(loss)
+
+
+def label_argmax(onehot, theta, out_size=None, precision="f32"):
+    """get_argmaxed_segs(grid_sample(onehot, affine_grid(theta), mode="nearest", zeros)) — torch_utils.py:71-82."""
+    oh, theta = _f32(onehot), _f32(theta)
+    B, L, Di, Hi, Wi = oh.shape
+    Do, Ho, Wo = [int(v) for v in (out_size[-3:] if out_size is not None else oh.shape[-3:])]
+    out = np.empty((B, 1, Do, Ho, Wo), np.int64)
+    fn = getattr(lib(), f"oracle_label_argmax_{precision}")
+    fn.restype = ctypes.c_int
+    fn(_ptr(oh), _ptr(theta), out.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), B, L, Di, Hi, Wi, Do, Ho, Wo)
+    return out

@@ -328,6 +328,122 @@ int FN(oracle_affine_sample_bwd_input)(const float *grad_out, const float *theta
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Consistency loss of the TTA step.  Reference: dg_tta/tta/tta.py:263-269 and soft_dice_loss,
+ * dg_tta/tta/torch_utils.py:90-104.
+ *   :264-266  mask = (sum_c a > 0) * (sum_c b > 0)
+ *   :267-268  sm_x = softmax_c(x) * mask
+ *   torch_utils.py:94-95   nominator = mean_v 2 sm_a sm_b ; denominator = 0.5 mean_v (sm_a + sm_b)^2
+ *   :97-102   dice = 1 if denominator.sum() == 0 else nominator / denominator     (per sample and class)
+ *   tta.py:269  loss = 1 - mean(dice[:, start_class:])
+ * Returns the loss; grad_a (may be NULL) receives d loss / d target_a (the mask carries no gradient).
+ * ------------------------------------------------------------------------------------------------ */
+REAL FN(oracle_consistency_loss)(const float *ta, const float *tb, REAL *grad_a, int B, int C, long V, int start_class)
+{
+    REAL *nom = (REAL *)calloc((size_t)B * C, sizeof(REAL)), *den = (REAL *)calloc((size_t)B * C, sizeof(REAL));
+    REAL *pa = (REAL *)malloc((size_t)C * sizeof(REAL)), *pb = (REAL *)malloc((size_t)C * sizeof(REAL));
+    for (int b = 0; b < B; ++b)
+        for (long v = 0; v < V; ++v) {
+            REAL sa = 0, sb = 0, ma = -INFINITY, mb = -INFINITY;
+            for (int c = 0; c < C; ++c) {
+                const REAL xa = ta[((long)b * C + c) * V + v], xb = tb[((long)b * C + c) * V + v];
+                sa += xa; sb += xb;
+                if (xa > ma) ma = xa;
+                if (xb > mb) mb = xb;
+            }
+            if (!(sa > 0 && sb > 0)) continue;
+            REAL ea = 0, eb = 0;
+            for (int c = 0; c < C; ++c) {
+                pa[c] = (REAL)EXPFN(ta[((long)b * C + c) * V + v] - ma); ea += pa[c];
+                pb[c] = (REAL)EXPFN(tb[((long)b * C + c) * V + v] - mb); eb += pb[c];
+            }
+            for (int c = 0; c < C; ++c) {
+                const REAL a = pa[c] / ea, bb = pb[c] / eb;
+                nom[b * C + c] += 2 * a * bb;
+                den[b * C + c] += (a + bb) * (a + bb);
+            }
+        }
+    REAL dsum = 0;
+    for (int i = 0; i < B * C; ++i) { nom[i] /= (REAL)V; den[i] = (REAL)0.5 * den[i] / (REAL)V; dsum += den[i]; }
+    const int K = B * (C - start_class);
+    REAL loss = 1;
+    for (int b = 0; b < B; ++b)
+        for (int c = start_class; c < C; ++c) loss -= (dsum == 0 ? (REAL)1 : nom[b * C + c] / den[b * C + c]) / (REAL)K;
+    if (grad_a) {
+        for (long i = 0; i < (long)B * C * V; ++i) grad_a[i] = 0;
+        if (dsum != 0)
+            for (int b = 0; b < B; ++b)
+                for (long v = 0; v < V; ++v) {
+                    REAL sa = 0, sb = 0, ma = -INFINITY, mb = -INFINITY;
+                    for (int c = 0; c < C; ++c) {
+                        const REAL xa = ta[((long)b * C + c) * V + v], xb = tb[((long)b * C + c) * V + v];
+                        sa += xa; sb += xb;
+                        if (xa > ma) ma = xa;
+                        if (xb > mb) mb = xb;
+                    }
+                    if (!(sa > 0 && sb > 0)) continue;
+                    REAL ea = 0, eb = 0;
+                    for (int c = 0; c < C; ++c) {
+                        pa[c] = (REAL)EXPFN(ta[((long)b * C + c) * V + v] - ma); ea += pa[c];
+                        pb[c] = (REAL)EXPFN(tb[((long)b * C + c) * V + v] - mb); eb += pb[c];
+                    }
+                    REAL dot = 0;
+                    for (int c = 0; c < C; ++c) {
+                        pa[c] /= ea; pb[c] /= eb;
+                        /* d loss / d sm_a[c]: loss = 1 - (1/K) sum_{c >= start} nom_c / den_c,
+                         * nom_c = (1/V) sum 2 a b, den_c = (0.5/V) sum (a+b)^2 */
+                        REAL q = 0;
+                        if (c >= start_class) {
+                            const REAL n = nom[b * C + c], dn = den[b * C + c];
+                            q = -((REAL)1 / (REAL)K) * ((2 * pb[c] / (REAL)V) / dn - n * ((pa[c] + pb[c]) / (REAL)V) / (dn * dn));
+                        }
+                        pb[c] = q;
+                        dot += pa[c] * q;
+                    }
+                    for (int c = 0; c < C; ++c) grad_a[((long)b * C + c) * V + v] = pa[c] * (pb[c] - dot);
+                }
+    }
+    free(nom); free(den); free(pa); free(pb);
+    return loss;
+}
+
+/* Label crop of get_batch.  Reference: dg_tta/tta/torch_utils.py:71-73 (grid_sample, mode="nearest", zeros padding, of
+ * the one-hot label channels through the patch affine) and :79-82 (get_argmaxed_segs: background channel where the
+ * labels sum to < 1, then argmax; lowest index wins ties). */
+int FN(oracle_label_argmax)(const float *onehot, const float *theta, long long *out, int B, int L, int Di, int Hi, int Wi,
+                            int Do, int Ho, int Wo)
+{
+    const long Vi = (long)Di * Hi * Wi, Vo = (long)Do * Ho * Wo;
+    for (int b = 0; b < B; ++b) {
+        const float *th = theta + b * 12;
+        for (int d = 0; d < Do; ++d)
+            for (int h = 0; h < Ho; ++h)
+                for (int w = 0; w < Wo; ++w) {
+                    const REAL xn = FN(base_coord)(w, Wo), yn = FN(base_coord)(h, Ho), zn = FN(base_coord)(d, Do);
+                    const REAL gx = (REAL)th[0] * xn + (REAL)th[1] * yn + (REAL)th[2] * zn + (REAL)th[3];
+                    const REAL gy = (REAL)th[4] * xn + (REAL)th[5] * yn + (REAL)th[6] * zn + (REAL)th[7];
+                    const REAL gz = (REAL)th[8] * xn + (REAL)th[9] * yn + (REAL)th[10] * zn + (REAL)th[11];
+                    const REAL rx = NEARBY(FN(unnormalize)(gx, Wi)), ry = NEARBY(FN(unnormalize)(gy, Hi)),
+                               rz = NEARBY(FN(unnormalize)(gz, Di));
+                    long long label = 0;
+                    if (rx >= 0 && rx < Wi && ry >= 0 && ry < Hi && rz >= 0 && rz < Di) {
+                        const long off = ((long)rz * Hi + (long)ry) * Wi + (long)rx;
+                        REAL sum = 0, best = -INFINITY;
+                        int arg = 0;
+                        for (int l = 0; l < L; ++l) {
+                            const REAL v = onehot[((long)b * L + l) * Vi + off];
+                            sum += v;
+                            if (v > best) { best = v; arg = l + 1; }
+                        }
+                        const REAL bg = sum < 1 ? (REAL)1 : (REAL)0;
+                        label = bg >= best ? 0 : arg;
+                    }
+                    out[(long)b * Vo + ((long)d * Ho + h) * Wo + w] = label;
+                }
+    }
+    return 0;
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

@@ -75,3 +75,31 @@ def test_gradient_for_both_branches_and_empty_overlap():
     # no common content at all: denominator.sum() == 0 -> dice = 1 -> loss = 0 (torch_utils.py:97-98)
     z = torch.zeros(1, 6, 4, 4, 4, device="cuda")
     assert float(consistency_dice_loss(z, z)) == 0.0
+
+
+def test_against_the_c_oracle_fp64_truth():
+    """CUDA path vs the plain-C restatement evaluated in double precision (oracle/dgtta_oracle_impl.h)"""
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss
+    from oracle import cform
+    g = torch.Generator().manual_seed(12)
+    a = torch.randn(2, 9, 14, 18, 20, generator=g) * 3 + 0.2
+    b = torch.randn(2, 9, 14, 18, 20, generator=g) * 3 + 0.2
+    a[:, :, -2:] = 0.0
+    truth_loss, truth_grad = cform.consistency_loss(a.numpy(), b.numpy(), precision="f64")
+    ad = a.cuda().requires_grad_(True)
+    loss = consistency_dice_loss(ad, b.cuda())
+    loss.backward()
+    assert abs(loss.item() - truth_loss) <= 1e-5
+    assert np.abs(ad.grad.cpu().numpy() - truth_grad).max() <= 2e-5 * np.abs(truth_grad).max()
+
+
+def test_label_argmax_against_the_c_oracle():
+    from dg_tta_b200.tta.augmentation_utils import affine_label_argmax, get_rand_affine
+    from oracle import cform
+    g = torch.Generator().manual_seed(5)
+    lab = (torch.rand(2, 6, 16, 18, 20, generator=g) > 0.75).float()
+    torch.manual_seed(8)
+    R, _ = get_rand_affine(2, strength=0.15)
+    got = affine_label_argmax(lab.cuda(), R, (12, 20, 9)).cpu().numpy()
+    ref = cform.label_argmax(lab.numpy(), R.numpy(), (12, 20, 9))
+    assert (got != ref).mean() <= 0.002          # nearest-neighbour ties at .5 may round differently in 1e-7 coordinates

@@ -174,3 +174,29 @@ def test_argmaxed_segs_port_matches_reference_fixture():
     from oracle import ref_port
     g = load_golden("argmaxed_segs")
     assert np.array_equal(ref_port.argmaxed_segs(torch.from_numpy(g["segs"])).numpy(), g["out"])
+
+
+def test_consistency_loss_c_oracle_matches_reference_fixture():
+    g = load_golden("consistency")
+    scale = np.abs(g["grad_a"]).max()
+    for precision in ("f32", "f64"):                       # the fixture itself is fp32 torch
+        loss, grad = cform.consistency_loss(g["target_a"], g["target_b"], precision=precision)
+        assert abs(loss - float(g["loss"])) <= 2e-6
+        assert np.abs(grad - g["grad_a"]).max() <= 1e-5 * scale
+
+
+def test_label_argmax_c_oracle_matches_reference_fixture():
+    g = load_golden("argmaxed_segs")
+    theta = np.eye(3, 4, dtype=np.float32)[None]
+    assert np.array_equal(cform.label_argmax(g["segs"], theta), g["out"])
+    # and the reference crops of get_batch (nearest sampling + argmax through a real patch affine)
+    gb = load_golden("get_batch")
+    sample = gb["sample"]
+    onehot = sample[1:][None]
+    out = cform.label_argmax(onehot, theta, gb["lbl_c"].shape)   # centre crop = scale-only affine
+    import torch
+    t_patch = torch.as_tensor(gb["patch"].tolist(), dtype=torch.float32)
+    t_in = torch.as_tensor(sample.shape[-3:], dtype=torch.float32)
+    aff = torch.cat([(t_patch / t_in).flip(0), torch.tensor([1.0])]).diag()[:3][None].numpy()
+    out = cform.label_argmax(onehot, aff, gb["lbl_c"].shape)
+    assert (out != gb["lbl_c"]).mean() <= 0.002
