@@ -36,6 +36,11 @@ SIGNATURES = {
     "dgtta_consistency_sums_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "dgtta_consistency_sums_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "dgtta_affine_label_argmax": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "dgtta_label_map_from_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
+    "dgtta_affine_label_gather": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "dgtta_affine_crop_shifted_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "dgtta_volume_min_workspace_bytes": (c_size_t, []),
+    "dgtta_volume_min": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 

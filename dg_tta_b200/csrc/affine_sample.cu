@@ -4,8 +4,11 @@
 // tta.py:571-575 (inverse warp of the prediction, zeros padding, autograd w.r.t. the input) and
 // dg_tta/tta/torch_utils.py:55-73 (patch crop; nearest for labels).  align_corners=False throughout.
 // Coordinates follow torch (third party; ATen/native/AffineGridGenerator.cpp, GridSampler.h):
-//     base_i = linspace(-1, 1, N)[i] * (N-1) / N          (linspace evaluated from both ends)
-//     (gx,gy,gz) = theta[b] . (base_w, base_h, base_d, 1)
+//     base_i = linspace(-1, 1, N)[i] * (N-1) / N          linspace: fma(step, i, -1) below N/2, fma(-step, N-1-i, 1) above
+//     (gx,gy,gz) = base @ theta[b]^T                      K = 4 accumulated in order with FMAs: fma(z,t2, fma(y,t1, x*t0)) + t3
+//   — the rounding sequence torch's kernels execute (RangeFactories linspace, tensor mul / true div, bmm), reproduced
+//   operation by operation so that mode="nearest" picks the same source voxel on .5 ties: bit-exact index work
+//   (tests/test_sampler_gpu.py compares the label crops with np.array_equal against the reference's outputs).
 //     ix = ((gx + 1) * W_in - 1) / 2 ; border: clamp to [0, W_in-1] ; zeros: corners outside contribute 0
 // No grid tensor is ever materialised (the reference builds three 12 B/voxel grids per warp).
 #include "common.cuh"
@@ -16,16 +19,27 @@ struct SampleParams {
     const float *in;
     const float *theta;
     float *out;
+    const float *bias;      // NULL, or [B]: out = sample(in - bias[b]) + bias[b]  (get_batch's min shift, torch_utils.py:58-62)
     int B, C, Di, Hi, Wi, Do, Ho, Wo;
+    // launch-constant pieces of the base-grid arithmetic, computed on the host with the same IEEE operations:
+    float step_w, step_h, step_d;   // 2 / (n - 1)
+    float rcp_w, rcp_h, rcp_d;      // RN(1 / n)
+    int exact_div;                  // some n > DIVC_MAX_N: use the IEEE division instead of the corrected reciprocal
 };
 
-__device__ __forceinline__ float base_coord(int i, int n)
+// x / n, correctly rounded, without the division subroutine: q = RN(x * r), r = RN(1/n); residual e = fma(-q, n, x) is
+// exact; RN(q + e * r) is the correctly rounded quotient (Markstein).  Checked exhaustively against IEEE division for
+// every base-grid value of every n <= 4096 (tools/check_divc.py); larger n take __fdiv_rn.
+constexpr int DIVC_MAX_N = 4096;
+
+__device__ __forceinline__ float base_coord(int i, int n, float step, float rcp, int exact_div)
 {
     if (n <= 1) return 0.f;
-    const float step = __fdiv_rn(2.f, (float)(n - 1));
-    const float v = (i < n / 2) ? __fadd_rn(-1.f, __fmul_rn(step, (float)i))
-                                : __fsub_rn(1.f, __fmul_rn(step, (float)(n - 1 - i)));
-    return __fdiv_rn(__fmul_rn(v, (float)(n - 1)), (float)n);
+    const float v = (i < n / 2) ? __fmaf_rn(step, (float)i, -1.f) : __fmaf_rn(-step, (float)(n - 1 - i), 1.f);
+    const float m = __fmul_rn(v, (float)(n - 1));
+    if (exact_div) return __fdiv_rn(m, (float)n);
+    const float q = __fmul_rn(m, rcp);
+    return __fmaf_rn(__fmaf_rn(-q, (float)n, m), rcp, q);
 }
 
 __device__ __forceinline__ float unnormalize(float g, int size)
@@ -39,37 +53,25 @@ struct Coords {
     float ix, iy, iz;
 };
 
-// Block = 32 (w) x 8 (h) output voxels of one d-plane; the per-axis base coordinates (two IEEE divisions each)
-// are tabulated once per block in shared memory instead of being recomputed per voxel.
+// Block = 32 (w) x 8 (h) output voxels of one d-plane.  Every thread derives its own three base coordinates (a dozen
+// FP32 instructions, no division subroutine, no shared-memory table, no barrier).
 constexpr int SBX = 32, SBY = 8;
 constexpr int SAMPLE_THREADS = SBX * SBY;
 
-struct BlockCoords {
-    float th[12];
-    float bx[SBX];
-    float by[SBY];
-    float bz;
-};
-
-__device__ __forceinline__ void block_setup(const SampleParams &P, BlockCoords &S, int b, int w0, int h0, int d)
-{
-    const int t = threadIdx.y * SBX + threadIdx.x;
-    if (t < 12) S.th[t] = P.theta[b * 12 + t];
-    if (t >= 32 && t < 32 + SBX) S.bx[t - 32] = base_coord(min(w0 + t - 32, P.Wo - 1), P.Wo);
-    if (t >= 64 && t < 64 + SBY) S.by[t - 64] = base_coord(min(h0 + t - 64, P.Ho - 1), P.Ho);
-    if (t == 96) S.bz = base_coord(d, P.Do);
-    __syncthreads();
-}
-
 template <int PAD>
-__device__ __forceinline__ Coords source_coords(const SampleParams &P, const BlockCoords &S)
+__device__ __forceinline__ Coords source_coords(const SampleParams &P, int b, int w, int h, int d)
 {
-    const float *th = S.th;
-    const float xn = S.bx[threadIdx.x], yn = S.by[threadIdx.y], zn = S.bz;
-    // row-times-column products summed left to right, like the reference's base_grid @ theta^T
-    const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[0], xn), __fmul_rn(th[1], yn)), __fmul_rn(th[2], zn)), th[3]);
-    const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[4], xn), __fmul_rn(th[5], yn)), __fmul_rn(th[6], zn)), th[7]);
-    const float gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(th[8], xn), __fmul_rn(th[9], yn)), __fmul_rn(th[10], zn)), th[11]);
+    const float *th = P.theta + b * 12;
+    const float xn = base_coord(min(w, P.Wo - 1), P.Wo, P.step_w, P.rcp_w, P.exact_div);
+    const float yn = base_coord(min(h, P.Ho - 1), P.Ho, P.step_h, P.rcp_h, P.exact_div);
+    const float zn = base_coord(d, P.Do, P.step_d, P.rcp_d, P.exact_div);
+    float t[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) t[k] = __ldg(th + k);
+    // base_grid @ theta^T: the K = 4 products accumulated in order, first one rounded, the rest fused (see header)
+    const float gx = __fadd_rn(__fmaf_rn(zn, t[2], __fmaf_rn(yn, t[1], __fmul_rn(xn, t[0]))), t[3]);
+    const float gy = __fadd_rn(__fmaf_rn(zn, t[6], __fmaf_rn(yn, t[5], __fmul_rn(xn, t[4]))), t[7]);
+    const float gz = __fadd_rn(__fmaf_rn(zn, t[10], __fmaf_rn(yn, t[9], __fmul_rn(xn, t[8]))), t[11]);
     Coords c;
     c.ix = unnormalize(gx, P.Wi); c.iy = unnormalize(gy, P.Hi); c.iz = unnormalize(gz, P.Di);
     if (PAD == DGTTA_PAD_BORDER) { c.ix = clip_coord(c.ix, P.Wi); c.iy = clip_coord(c.iy, P.Hi); c.iz = clip_coord(c.iz, P.Di); }
@@ -105,15 +107,13 @@ __device__ __forceinline__ Corners trilinear_corners(const SampleParams &P, cons
 template <int INTERP, int PAD>
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const __grid_constant__ SampleParams P)
 {
-    __shared__ BlockCoords S;
     const int ntw = (P.Wo + SBX - 1) / SBX;
     const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
     const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
-    block_setup(P, S, b, w0, h0, d);
     const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
     if (w >= P.Wo || h >= P.Ho) return;
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
-    const Coords c = source_coords<PAD>(P, S);
+    const Coords c = source_coords<PAD>(P, b, w, h, d);
     const float *src = P.in + (size_t)b * P.C * Vi;
     float *dst = P.out + (size_t)b * P.C * Vo + ((size_t)d * P.Ho + h) * P.Wo + w;
     if (INTERP == DGTTA_INTERP_NEAREST) {
@@ -127,6 +127,18 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_fwd_kernel(const
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if (q.off[k] < 0) { q.off[k] = 0; q.wgt[k] = 0.f; }
+    if (P.bias) {
+        // get_batch's image crop (torch_utils.py:58-62): grid_sample(vol - min, zeros) + min in one gather — the shift is
+        // applied to every in-bounds corner before the weighting, the out-of-bounds corners contribute 0 (their weight is 0)
+        const float bias = __ldg(P.bias + b);
+        for (int ch = 0; ch < P.C; ++ch) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(__fsub_rn(__ldg(src + (size_t)ch * Vi + q.off[k]), bias), q.wgt[k], acc);
+            __stcs(dst + (size_t)ch * Vo, __fadd_rn(acc, bias));
+        }
+        return;
+    }
     // channel loop: the eight corner offsets and weights stay in registers, only the two channel base pointers move
     // (one 64-bit add each per trip); four channels per trip keep 32 independent gathers in flight
     const float *cb = src;
@@ -172,16 +184,14 @@ template <int PAD>
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const __grid_constant__ SampleParams P)
 {
     // here P.in = grad_out [B,C,Do,Ho,Wo], P.out = grad_in [B,C,Di,Hi,Wi]
-    __shared__ BlockCoords S;
     const int ntw = (P.Wo + SBX - 1) / SBX;
     const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
     const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
-    block_setup(P, S, b, w0, h0, d);
     const int lane = threadIdx.x;   // blockDim.x == 32: a warp is one row of the block
     const int w = w0 + lane, h = h0 + threadIdx.y;
     const bool active = w < P.Wo && h < P.Ho;   // inactive lanes stay for the shuffles and contribute nothing
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
-    const Coords c = source_coords<PAD>(P, S);
+    const Coords c = source_coords<PAD>(P, b, w, h, d);
     Corners q = trilinear_corners(P, c);
     if (!active) {
 #pragma unroll
@@ -230,15 +240,13 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_sample_bwd_kernel(const
 // index like torch.argmax; the background channel is index 0.
 __global__ void __launch_bounds__(SAMPLE_THREADS) affine_label_argmax_kernel(const __grid_constant__ SampleParams P, long long *out)
 {
-    __shared__ BlockCoords S;
     const int ntw = (P.Wo + SBX - 1) / SBX;
     const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
     const int w0 = tw * SBX, h0 = th_ * SBY, d = blockIdx.y, b = blockIdx.z;
-    block_setup(P, S, b, w0, h0, d);
     const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
     if (w >= P.Wo || h >= P.Ho) return;
     const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
-    const Coords c = source_coords<DGTTA_PAD_ZEROS>(P, S);
+    const Coords c = source_coords<DGTTA_PAD_ZEROS>(P, b, w, h, d);
     const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
     const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
     long long label = 0;
@@ -258,8 +266,102 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) affine_label_argmax_kernel(con
     out[(size_t)b * Vo + ((size_t)d * P.Ho + h) * P.Wo + w] = label;
 }
 
+// Integer label path.  Nearest sampling picks ONE source voxel, and get_argmaxed_segs is a per-voxel
+// function of that voxel's L channel values, so the two commute: argmaxed(nearest_sample(onehot)) ==
+// nearest_sample(argmaxed(onehot)) with 0 (background) outside the volume.  label_map_kernel evaluates the per-voxel
+// rule once per volume (the host side caches it on the resident tensor); label_gather_kernel then crops from a
+// 2 B/voxel map instead of the L x 4 B/voxel one-hot volume (104 channels in the reference's TotalSegmentator tasks,
+// dg_tta/tta/nnunet_utils.py:191-195).
+__global__ void __launch_bounds__(256) label_map_kernel(const float *onehot, short *map, int L, long long V)
+{
+    const long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (v >= V) return;
+    const float *src = onehot + (size_t)b * L * V + v;
+    float sum = 0.f, best = -__int_as_float(0x7f800000);
+    int arg = 0;
+    for (int ch = 0; ch < L; ++ch) {
+        const float x = __ldg(src + (size_t)ch * V);
+        sum += x;                                   // torch's sum over dim 1 runs in channel order too
+        if (x > best) { best = x; arg = ch + 1; }
+    }
+    const float bg = sum < 1.0f ? 1.f : 0.f;
+    map[(size_t)b * V + v] = (short)(bg >= best ? 0 : arg);
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) label_gather_kernel(const __grid_constant__ SampleParams P, const short *map,
+                                                                      long long *out)
+{
+    const int ntw = (P.Wo + SBX - 1) / SBX;
+    const int tw = blockIdx.x % ntw, th_ = blockIdx.x / ntw;
+    const int w = tw * SBX + threadIdx.x, h = th_ * SBY + threadIdx.y, d = blockIdx.y, b = blockIdx.z;
+    if (w >= P.Wo || h >= P.Ho) return;
+    const size_t Vo = (size_t)P.Do * P.Ho * P.Wo, Vi = (size_t)P.Di * P.Hi * P.Wi;
+    const Coords c = source_coords<DGTTA_PAD_ZEROS>(P, b, w, h, d);
+    const float rx = nearbyintf(c.ix), ry = nearbyintf(c.iy), rz = nearbyintf(c.iz);
+    const bool ok = rx >= 0.f && rx < (float)P.Wi && ry >= 0.f && ry < (float)P.Hi && rz >= 0.f && rz < (float)P.Di;
+    long long label = 0;
+    if (ok) label = map[(size_t)b * Vi + ((size_t)(int)rz * P.Hi + (int)ry) * P.Wi + (int)rx];
+    out[(size_t)b * Vo + ((size_t)d * P.Ho + h) * P.Wo + w] = label;
+}
+
+// min over a volume (img.min() of torch_utils.py:58): warp-shuffle + block reduction to per-block partials, then one
+// block over the partials.  min is exact in any order, so the result is bitwise torch's.
+constexpr int MIN_BLOCKS = 592;   // 148 SMs x 4
+__global__ void __launch_bounds__(256) volume_min_partial_kernel(const float *in, long long n, float *partial)
+{
+    __shared__ float red[8];
+    float m = __int_as_float(0x7f800000);
+    bool nan = false;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) ? n / 4 : 0;
+    const float4 *in4 = reinterpret_cast<const float4 *>(in);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = __ldg(in4 + i);
+        m = fminf(fminf(m, v.x), fminf(fminf(v.y, v.z), v.w));
+        nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = __ldg(in + i);
+        m = fminf(m, v);
+        nan |= v != v;
+    }
+    if (nan) m = __int_as_float(0x7fc00000);      // torch.min propagates NaN; fminf would drop it
+    // NaN-propagating reduction: a NaN partial wins
+    auto comb = [](float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = comb(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 8 ? red[threadIdx.x] : __int_as_float(0x7f800000);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = comb(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) partial[blockIdx.x] = m;
+    }
+}
+__global__ void __launch_bounds__(1024) volume_min_final_kernel(const float *partial, int n, float *out)
+{
+    __shared__ float red[32];
+    auto comb = [](float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); };
+    float m = threadIdx.x < n ? partial[threadIdx.x] : __int_as_float(0x7f800000);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = comb(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = comb(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) out[0] = m;
+    }
+}
+
 void preload_sampler()
 {
+    DGTTA_TOUCH(label_map_kernel);
+    DGTTA_TOUCH(label_gather_kernel);
+    DGTTA_TOUCH(volume_min_partial_kernel);
+    DGTTA_TOUCH(volume_min_final_kernel);
     DGTTA_TOUCH(affine_label_argmax_kernel);
     DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_ZEROS>);
     DGTTA_TOUCH(affine_sample_fwd_kernel<DGTTA_INTERP_TRILINEAR, DGTTA_PAD_BORDER>);
@@ -283,6 +385,22 @@ static int sample_check(const void *a, const void *t, const void *o, int B, int 
     return 0;
 }
 
+static SampleParams make_params(const float *in, const float *theta, float *out, const float *bias, int B, int C, int Di, int Hi,
+                                int Wi, int Do, int Ho, int Wo)
+{
+    SampleParams P;
+    P.in = in; P.theta = theta; P.out = out; P.bias = bias;
+    P.B = B; P.C = C; P.Di = Di; P.Hi = Hi; P.Wi = Wi; P.Do = Do; P.Ho = Ho; P.Wo = Wo;
+    // volatile: keep the host compiler from folding these into anything but one IEEE division each
+    volatile float two = 2.f, one = 1.f;
+    P.step_w = Wo > 1 ? two / (float)(Wo - 1) : 0.f;
+    P.step_h = Ho > 1 ? two / (float)(Ho - 1) : 0.f;
+    P.step_d = Do > 1 ? two / (float)(Do - 1) : 0.f;
+    P.rcp_w = one / (float)Wo; P.rcp_h = one / (float)Ho; P.rcp_d = one / (float)Do;
+    P.exact_div = (Wo > DIVC_MAX_N || Ho > DIVC_MAX_N || Do > DIVC_MAX_N) ? 1 : 0;
+    return P;
+}
+
 static dim3 sample_grid(int B, int Do, int Ho, int Wo)
 {
     return dim3((unsigned)(((Wo + SBX - 1) / SBX) * ((Ho + SBY - 1) / SBY)), (unsigned)Do, (unsigned)B);
@@ -292,9 +410,27 @@ static dim3 sample_grid(int B, int Do, int Ho, int Wo)
 
 using namespace dgtta;
 
+static int sample_fwd(const float *in_dev, const float *theta_dev, const float *bias_dev, float *out_dev, int B, int C, int Di,
+                      int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding, dgtta_stream_t stream_);
+
 extern "C" int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_dev, float *out_dev, int B, int C,
                                        int Di, int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding,
                                        dgtta_stream_t stream_)
+{
+    return sample_fwd(in_dev, theta_dev, nullptr, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo, interp, padding, stream_);
+}
+
+extern "C" int dgtta_affine_crop_shifted_fwd(const float *in_dev, const float *theta_dev, const float *shift_dev, float *out_dev,
+                                             int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                                             dgtta_stream_t stream_)
+{
+    if (!shift_dev) { set_error("dgtta_affine_crop_shifted_fwd: null shift"); return DGTTA_ENULL; }
+    return sample_fwd(in_dev, theta_dev, shift_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo, DGTTA_INTERP_TRILINEAR,
+                      DGTTA_PAD_ZEROS, stream_);
+}
+
+static int sample_fwd(const float *in_dev, const float *theta_dev, const float *bias_dev, float *out_dev, int B, int C, int Di,
+                      int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding, dgtta_stream_t stream_)
 {
     int rc = sample_check(in_dev, theta_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo);
     if (rc) return rc;
@@ -304,7 +440,7 @@ extern "C" int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_d
         return DGTTA_EINVAL;
     }
     cudaStream_t stream = (cudaStream_t)stream_;
-    SampleParams P{in_dev, theta_dev, out_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
+    const SampleParams P = make_params(in_dev, theta_dev, out_dev, bias_dev, B, C, Di, Hi, Wi, Do, Ho, Wo);
     const dim3 grid = sample_grid(B, Do, Ho, Wo);
     const dim3 block(SBX, SBY, 1);
     if (interp == DGTTA_INTERP_TRILINEAR) {
@@ -327,7 +463,7 @@ extern "C" int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e = cudaMemsetAsync(grad_in_dev, 0, (size_t)B * C * Di * Hi * Wi * sizeof(float), stream);
     if (e != cudaSuccess) { set_error("dgtta_affine_sample_bwd_input: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    SampleParams P{grad_out_dev, theta_dev, grad_in_dev, B, C, Di, Hi, Wi, Do, Ho, Wo};
+    const SampleParams P = make_params(grad_out_dev, theta_dev, grad_in_dev, nullptr, B, C, Di, Hi, Wi, Do, Ho, Wo);
     const dim3 grid = sample_grid(B, Do, Ho, Wo);
     const dim3 block(SBX, SBY, 1);
     if (padding == DGTTA_PAD_ZEROS) affine_sample_bwd_kernel<DGTTA_PAD_ZEROS><<<grid, block, 0, stream>>>(P);
@@ -340,7 +476,43 @@ extern "C" int dgtta_affine_label_argmax(const float *onehot_dev, const float *t
 {
     int rc = sample_check(onehot_dev, theta_dev, out_dev, B, L, Di, Hi, Wi, Do, Ho, Wo);
     if (rc) return rc;
-    SampleParams P{onehot_dev, theta_dev, nullptr, B, L, Di, Hi, Wi, Do, Ho, Wo};
+    const SampleParams P = make_params(onehot_dev, theta_dev, nullptr, nullptr, B, L, Di, Hi, Wi, Do, Ho, Wo);
     affine_label_argmax_kernel<<<sample_grid(B, Do, Ho, Wo), dim3(SBX, SBY, 1), 0, (cudaStream_t)stream_>>>(P, out_dev);
     return check_launch("affine_label_argmax_kernel");
+}
+
+extern "C" int dgtta_label_map_from_onehot(const float *onehot_dev, short *map_dev, int B, int L, long long V,
+                                           dgtta_stream_t stream_)
+{
+    if (!onehot_dev || !map_dev) { set_error("dgtta_label_map_from_onehot: null pointer"); return DGTTA_ENULL; }
+    if (B <= 0 || B > 65535 || L <= 0 || L > 32766 || V <= 0 || V >= (1ll << 38)) { set_error("dgtta_label_map_from_onehot: bad shape"); return DGTTA_EINVAL; }
+    label_map_kernel<<<dim3((unsigned)((V + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream_>>>(onehot_dev, map_dev, L, V);
+    return check_launch("label_map_kernel");
+}
+
+extern "C" int dgtta_affine_label_gather(const short *map_dev, const float *theta_dev, long long *out_dev, int B, int Di, int Hi,
+                                         int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream_)
+{
+    int rc = sample_check(map_dev, theta_dev, out_dev, B, 1, Di, Hi, Wi, Do, Ho, Wo);
+    if (rc) return rc;
+    const SampleParams P = make_params(nullptr, theta_dev, nullptr, nullptr, B, 1, Di, Hi, Wi, Do, Ho, Wo);
+    label_gather_kernel<<<sample_grid(B, Do, Ho, Wo), dim3(SBX, SBY, 1), 0, (cudaStream_t)stream_>>>(P, map_dev, out_dev);
+    return check_launch("label_gather_kernel");
+}
+
+extern "C" size_t dgtta_volume_min_workspace_bytes(void) { return MIN_BLOCKS * sizeof(float); }
+
+extern "C" int dgtta_volume_min(const float *in_dev, long long numel, float *out_dev, void *workspace_dev, size_t workspace_bytes,
+                                dgtta_stream_t stream_)
+{
+    if (!in_dev || !out_dev || !workspace_dev) { set_error("dgtta_volume_min: null pointer"); return DGTTA_ENULL; }
+    if (numel <= 0) { set_error("dgtta_volume_min: empty input"); return DGTTA_EINVAL; }
+    if (workspace_bytes < MIN_BLOCKS * sizeof(float)) { set_error("dgtta_volume_min: workspace too small"); return DGTTA_EWORKSPACE; }
+    const long long want = (numel + 256 * 16 - 1) / (256 * 16);
+    const int blocks = (int)(want < 1 ? 1 : (want > MIN_BLOCKS ? MIN_BLOCKS : want));
+    volume_min_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(in_dev, numel, (float *)workspace_dev);
+    int rc = check_launch("volume_min_partial_kernel");
+    if (rc) return rc;
+    volume_min_final_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>((const float *)workspace_dev, blocks, out_dev);
+    return check_launch("volume_min_final_kernel");
 }

@@ -106,6 +106,74 @@ def affine_label_argmax(onehot, theta, out_size=None):
     return out
 
 
+def affine_label_gather(label_map, theta, out_size=None):
+    """Nearest-mode crop of an integer label map (see label_map_from_onehot): [B,D,H,W] int16 -> [B,1,*out_size] int64,
+    0 outside the volume.  Equal, voxel for voxel, to affine_label_argmax on the one-hot volume the map was built from."""
+    if not (isinstance(label_map, torch.Tensor) and label_map.is_cuda and label_map.dtype == torch.int16 and label_map.dim() == 4):
+        raise TypeError("label_map must be a CUDA int16 tensor [B,D,H,W] (label_map_from_onehot)")
+    B, Di, Hi, Wi = label_map.shape
+    size = tuple(int(v) for v in (out_size[-3:] if out_size is not None else label_map.shape[-3:]))
+    theta = _theta_on(label_map.device, theta, B)
+    m = label_map.contiguous()
+    with torch.cuda.device(m.device):
+        out = torch.empty((B, 1) + size, device=m.device, dtype=torch.int64)
+        rc = _lib.lib().dgtta_affine_label_gather(m.data_ptr(), theta.data_ptr(), out.data_ptr(), B, Di, Hi, Wi,
+                                                  size[0], size[1], size[2], _lib.stream_ptr())
+        _lib.check(rc, "dgtta_affine_label_gather")
+    return out
+
+
+def label_map_from_onehot(onehot):
+    """get_argmaxed_segs (dg_tta/tta/torch_utils.py:79-82) applied to a whole one-hot volume once: [B,L,D,H,W] float32
+    -> [B,D,H,W] int16 with 0 = background (the L channels sum to < 1), else 1 + argmax."""
+    _lib.require_cuda_f32(onehot, "onehot")
+    if onehot.dim() != 5:
+        raise ValueError("label_map_from_onehot expects [B,L,D,H,W]")
+    B, L = onehot.shape[:2]
+    x = onehot.contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty((B,) + tuple(x.shape[2:]), device=x.device, dtype=torch.int16)
+        rc = _lib.lib().dgtta_label_map_from_onehot(x.data_ptr(), out.data_ptr(), B, L, x[0, 0].numel(), _lib.stream_ptr())
+        _lib.check(rc, "dgtta_label_map_from_onehot")
+    return out
+
+
+def volume_min(x):
+    """x.min() as a 1-element CUDA tensor (two small kernels, no host sync); NaN-propagating like torch.min."""
+    _lib.require_cuda_f32(x, "x")
+    L = _lib.lib()
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+        nbytes = L.dgtta_volume_min_workspace_bytes()
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        _lib.check(L.dgtta_volume_min(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr()),
+                   "dgtta_volume_min")
+    return out
+
+
+def affine_crop_shifted(input, theta, shift, out_size=None):
+    """grid_sample(input - shift, affine_grid(theta), zeros) + shift in one gather (dg_tta/tta/torch_utils.py:58-62 with
+    shift = input.min()); shift: CUDA float32 tensor with one entry per sample.  No autograd (get_batch runs under
+    no_grad in the reference)."""
+    _lib.require_cuda_f32(input, "input")
+    _lib.require_cuda_f32(shift, "shift")
+    if input.dim() != 5:
+        raise ValueError("affine_crop_shifted expects [B,C,D,H,W]")
+    B, C, Di, Hi, Wi = input.shape
+    if shift.numel() != B:
+        raise ValueError("shift must have one entry per sample")
+    size = tuple(int(v) for v in (out_size[-3:] if out_size is not None else input.shape[-3:]))
+    theta = _theta_on(input.device, theta, B)
+    x = input.contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, C) + size, device=x.device, dtype=torch.float32)
+        rc = _lib.lib().dgtta_affine_crop_shifted_fwd(x.data_ptr(), theta.data_ptr(), shift.contiguous().data_ptr(), out.data_ptr(),
+                                                     B, C, Di, Hi, Wi, size[0], size[1], size[2], _lib.stream_ptr())
+        _lib.check(rc, "dgtta_affine_crop_shifted_fwd")
+    return out
+
+
 _SIDE_STREAMS = {}
 
 

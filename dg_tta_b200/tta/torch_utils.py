@@ -10,62 +10,119 @@ Volumes may already live on the device: the reference re-uploads the whole volum
 import torch
 
 from .. import _lib
-from .augmentation_utils import affine_grid_sample, affine_label_argmax
+from .augmentation_utils import (affine_crop_shifted, affine_grid_sample, affine_label_argmax, affine_label_gather,
+                                 label_map_from_onehot, volume_min)
 
 
 def get_argmaxed_segs(segs):
-    """torch_utils.py:79-82: prepend a background channel (no label set) and take the argmax."""
-    segs_oh_w_bg = torch.cat([(segs.sum(1, keepdim=True) < 1.0).float(), segs], dim=1)
-    return segs_oh_w_bg.argmax(1, keepdim=True)
+    """Same result as torch_utils.py:79-82 ([B,L,D,H,W] one-hot -> [B,1,D,H,W] int64: 0 where the L channels sum to
+    < 1, else 1 + argmax, lowest index on ties), evaluated by the label-map kernel in one pass instead of
+    sum / cat / argmax over an (L+1)-channel copy."""
+    return label_map_from_onehot(segs)[:, None].long()
+
+
+class _ResidentVolume:
+    """Per-volume state get_batch needs on every call but which only depends on the volume: the device copy of the
+    image channel, its minimum (torch_utils.py:58) and the int16 label map that replaces the one-hot channels
+    (torch_utils.py:71-82, see augmentation_utils.label_map_from_onehot).  The reference recomputes / re-uploads all of
+    it per call (SURVEY.md §7 hard part 8)."""
+    __slots__ = ("version", "device", "img", "img_min", "label_map", "ref")
+
+    def __init__(self, data, device):
+        self.version = data._version
+        self.device = device
+        d = data.to(device=device, dtype=torch.float32)
+        self.img = d[0][None, None].contiguous()
+        self.img_min = volume_min(self.img)
+        self.label_map = label_map_from_onehot(d[1:][None]) if d[1:].numel() else None
+
+
+_RESIDENT = {}
+_RESIDENT_MAX = 16
+
+
+def resident_volume(data, device):
+    """Cached _ResidentVolume of a sample tensor ([1+L, D, H, W], CPU or CUDA).  Keyed on the tensor object (weak
+    reference: the entry dies with the tensor) and its version counter (in-place edits rebuild it)."""
+    import weakref
+    key = (id(data), str(device))
+    ent = _RESIDENT.get(key)
+    if ent is not None and ent.ref() is data and ent.version == data._version:
+        return ent
+    ent = _ResidentVolume(data, device)
+    ent.ref = weakref.ref(data, lambda _r, k=key: _RESIDENT.pop(k, None))
+    if len(_RESIDENT) >= _RESIDENT_MAX:
+        _RESIDENT.pop(next(iter(_RESIDENT)))
+    _RESIDENT[key] = ent
+    return ent
+
+
+def release_resident_volumes():
+    _RESIDENT.clear()
+
+
+def patch_affines(input_shape, patch_size, n, fixed_patch_idx=None):
+    """The host arithmetic of get_batch (torch_utils.py:23-45): n patch affines [n,3,4] (CPU float32) for crops of
+    `patch_size` out of a volume of `input_shape`, drawing `2*rand(3)-1` per patch from the CPU generator in the
+    reference's order (no draw for the centre crop)."""
+    t_patch_size = torch.as_tensor(patch_size)
+    t_input_shape = torch.as_tensor(tuple(input_shape))
+    scales = t_patch_size / t_input_shape
+    scales = torch.cat([scales.flip(0), torch.tensor([1.0])], dim=0)
+    patch_affine = scales.diag()
+    thetas = []
+    for _ in range(n):
+        if fixed_patch_idx == "center":
+            pass
+        else:
+            rand_offset = 2.0 * torch.rand(3) - 1.0
+            offset_range = ((t_input_shape - t_patch_size) / t_input_shape).clip(min=0.0)
+            ranged_offset = torch.cat([(rand_offset * offset_range).flip(0), torch.tensor([1.0])], dim=0)
+            patch_affine[:, -1] = ranged_offset
+        thetas.append(patch_affine[:3].clone())
+    return torch.stack(thetas).to(torch.float32)
 
 
 def get_batch(tensor_list, batch_idxs, patch_size, fixed_patch_idx=None, device="cuda"):
     """Same arguments and return value as the reference: (list of [1,1,*patch] image patches, list of
-    [1,1,*patch] int64 label patches or None).  `device` must be a CUDA device (no CPU fallback)."""
+    [1,1,*patch] int64 label patches or None).  `device` must be a CUDA device (no CPU fallback).
+
+    Per call and batch element this is two small gathers: the image crop with the `- min ... + min` shift folded in
+    (one kernel, the minimum cached per volume) and the label crop from the cached int16 label map."""
     assert fixed_patch_idx in range(8) or fixed_patch_idx is None or fixed_patch_idx == "center"
     device = torch.device(device)
     if device.type != "cuda":
         raise TypeError("dg_tta_b200.get_batch samples on a CUDA device; there is no CPU path")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     B = len(batch_idxs)
     b_img, b_label = [], []
-    t_patch_size = torch.as_tensor(patch_size)
-    t_input_shape = torch.as_tensor(tensor_list[0].shape[-3:])
-    scales = t_patch_size / t_input_shape
-    scales = torch.cat([scales.flip(0), torch.tensor([1.0])], dim=0)
-    patch_affine = scales.diag()
     out_size = (int(patch_size[0]), int(patch_size[1]), int(patch_size[2]))
+    thetas = patch_affines(tensor_list[0].shape[-3:], patch_size, B, fixed_patch_idx)
     with torch.no_grad():
         for b in range(B):
-            data = tensor_list[batch_idxs[b]]
-            if fixed_patch_idx == "center":
-                pass
-            else:
-                rand_offset = 2.0 * torch.rand(3) - 1.0
-                offset_range = ((t_input_shape - t_patch_size) / t_input_shape).clip(min=0.0)
-                ranged_offset = torch.cat([(rand_offset * offset_range).flip(0), torch.tensor([1.0])], dim=0)
-                patch_affine[:, -1] = ranged_offset
-            theta = patch_affine[:3][None]
-            data = data.to(device=device, dtype=torch.float32)
-            img = data[0][None, None]
-            img_min = img.min()
-            img_patch = affine_grid_sample(img - img_min, theta, out_size, padding_mode="zeros") + img_min
-            b_img.append(img_patch)
-            if data[1:].numel() == 0:
+            vol = resident_volume(tensor_list[batch_idxs[b]], device)
+            theta = thetas[b][None]
+            b_img.append(affine_crop_shifted(vol.img, theta, vol.img_min, out_size))
+            if vol.label_map is None:
                 b_label.append(None)   # no GT label available for this sample
             else:
-                # nearest-mode crop of the one-hot channels + background + argmax (:71-82), fused: no L-channel patch
-                b_label.append(affine_label_argmax(data[1:][None], theta, out_size))
+                b_label.append(affine_label_gather(vol.label_map, theta, out_size))
     return b_img, b_label
 
 
 def soft_dice_loss(smp_a, smp_b):
-    """torch_utils.py:90-104, unchanged (torch ops): per-(sample, class) soft Dice of two masked softmax maps."""
-    B, _, D, H, W = smp_a.shape
-    nominator = (2.0 * smp_a * smp_b).reshape(B, -1, D * H * W).mean(2)
-    denominator = 0.5 * ((smp_a + smp_b) ** 2).reshape(B, -1, D * H * W).mean(2)
-    if denominator.sum() == 0.0:
-        return (nominator * 0.0) + 1.0
-    return nominator / denominator   # "Do not add an eps here, it disturbs the consistency"
+    """Per-(sample, class) soft Dice of two probability maps, the quantity torch_utils.py:90-104 returns:
+    dice[b,c] = mean_v(2 a b) / (0.5 mean_v((a+b)^2)), all ones when every denominator is 0, no epsilon.  API mirror
+    for callers that already hold the two masked softmax maps; the TTA step itself uses consistency_dice_loss, which
+    never materialises them."""
+    n_vox = smp_a[0, 0].numel()
+    a, b = smp_a.flatten(2), smp_b.flatten(2)
+    num = (a * b).mul(2.0).sum(2) / n_vox
+    den = (a + b).square().sum(2).mul(0.5) / n_vox
+    if bool(den.sum() == 0.0):
+        return torch.ones_like(num)
+    return num / den
 
 
 class _ConsistencySums(torch.autograd.Function):

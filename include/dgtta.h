@@ -135,6 +135,26 @@ int dgtta_affine_sample_bwd_input(const float *grad_out_dev, const float *theta_
 int dgtta_affine_label_argmax(const float *onehot_dev, const float *theta_dev, long long *out_dev, int B, int L, int Di,
                               int Hi, int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream);
 
+/* Integer label path of the same crop.  Nearest sampling selects one source voxel and
+ * get_argmaxed_segs is a per-voxel function, so the crop commutes with it: build the label map of a volume once
+ * (dgtta_label_map_from_onehot: map[b,v] = 0 where the L channels sum to < 1, else 1 + argmax_l, the rule above) and
+ * crop from the 2 B/voxel map (dgtta_affine_label_gather; 0 outside the volume) instead of reading the L x 4 B/voxel
+ * one-hot volume (nnunet_utils.py:191-195 builds it with L = 104) on every call.
+ *   onehot_dev [B,L,V] float32 -> map_dev [B,V] int16 (L <= 32766);   map_dev [B,Di,Hi,Wi] -> out_dev [B,1,Do,Ho,Wo] int64 */
+int dgtta_label_map_from_onehot(const float *onehot_dev, short *map_dev, int B, int L, long long V, dgtta_stream_t stream);
+int dgtta_affine_label_gather(const short *map_dev, const float *theta_dev, long long *out_dev, int B, int Di, int Hi, int Wi,
+                              int Do, int Ho, int Wo, dgtta_stream_t stream);
+
+/* Image crop of get_batch in one gather.  Replaces `grid_sample(vol - vol.min(), zeros) + vol.min()`
+ * (dg_tta/tta/torch_utils.py:58-62): out = sum_k w_k (in[k] - shift[b]) + shift[b] over the in-bounds corners.
+ * dgtta_volume_min computes shift = min(in) (NaN-propagating like torch.min) into out_dev[0];
+ * workspace: dgtta_volume_min_workspace_bytes() bytes. */
+int dgtta_affine_crop_shifted_fwd(const float *in_dev, const float *theta_dev, const float *shift_dev, float *out_dev, int B,
+                                  int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo, dgtta_stream_t stream);
+size_t dgtta_volume_min_workspace_bytes(void);
+int dgtta_volume_min(const float *in_dev, long long numel, float *out_dev, void *workspace_dev, size_t workspace_bytes,
+                     dgtta_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Consistency-loss reductions of the TTA step.  Replace the elementwise chain of dg_tta/tta/tta.py:263-268

@@ -29,16 +29,19 @@ void oracle_mind_shift_table(int *shift1, int *shift2)
 #define EXPFN expf
 #define FLOORFN floorf
 #define NEARBY nearbyintf
+#define FMAFN fmaf
 #include "dgtta_oracle_impl.h"
 #undef REAL
 #undef SUFFIX
 #undef EXPFN
 #undef FLOORFN
 #undef NEARBY
+#undef FMAFN
 
 #define REAL double
 #define SUFFIX _f64
 #define EXPFN exp
 #define FLOORFN floor
 #define NEARBY nearbyint
+#define FMAFN fma
 #include "dgtta_oracle_impl.h"

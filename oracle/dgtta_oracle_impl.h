@@ -228,11 +228,21 @@ int FN(oracle_gin)(const float *x, REAL *out, const float *params, const int *ks
  * ------------------------------------------------------------------------------------------------ */
 static inline REAL FN(base_coord)(int i, int n)
 {
-    /* torch.linspace(-1, 1, n)[i] * (n-1)/n ; linspace is evaluated symmetrically from both ends */
+    /* torch.linspace(-1, 1, n)[i] * (n-1)/n.  linspace (ATen RangeFactories) is evaluated symmetrically from both ends
+     * with one fused multiply-add per element; then a tensor multiply and a true division, each rounded.  Checked
+     * bit for bit against torch (CPU build) for n = 2..399 while writing this oracle. */
     if (n <= 1) return (REAL)0;
     const REAL step = (REAL)2 / (REAL)(n - 1);
-    const REAL v = (i < n / 2) ? ((REAL)-1 + step * (REAL)i) : ((REAL)1 - step * (REAL)(n - 1 - i));
+    const REAL v = (i < n / 2) ? FMAFN(step, (REAL)i, (REAL)-1) : FMAFN(-step, (REAL)(n - 1 - i), (REAL)1);
     return v * (REAL)(n - 1) / (REAL)n;
+}
+
+/* one row of grid = base_grid.view(N, DHW, 4).bmm(theta^T) (AffineGridGenerator.cpp): the K = 4 products accumulated
+ * in order, the first rounded and the rest fused — the sequence the BLAS kernel executes (bit-exact vs torch's CPU
+ * affine_grid on random affines and sizes, 0 differing elements) */
+static inline REAL FN(grid_row)(const float *t, REAL xn, REAL yn, REAL zn)
+{
+    return FMAFN(zn, (REAL)t[2], FMAFN(yn, (REAL)t[1], xn * (REAL)t[0])) + (REAL)t[3];
 }
 
 static inline REAL FN(unnormalize)(REAL g, int size) { return ((g + (REAL)1) * (REAL)size - (REAL)1) / (REAL)2; }
@@ -255,9 +265,9 @@ int FN(oracle_affine_sample)(const float *in, const float *theta, REAL *out, int
         for (int h = 0; h < Ho; ++h)
             for (int w = 0; w < Wo; ++w) {
                 const REAL xn = FN(base_coord)(w, Wo), yn = FN(base_coord)(h, Ho), zn = FN(base_coord)(d, Do);
-                REAL gx = (REAL)th[0] * xn + (REAL)th[1] * yn + (REAL)th[2] * zn + (REAL)th[3];
-                REAL gy = (REAL)th[4] * xn + (REAL)th[5] * yn + (REAL)th[6] * zn + (REAL)th[7];
-                REAL gz = (REAL)th[8] * xn + (REAL)th[9] * yn + (REAL)th[10] * zn + (REAL)th[11];
+                REAL gx = FN(grid_row)(th + 0, xn, yn, zn);
+                REAL gy = FN(grid_row)(th + 4, xn, yn, zn);
+                REAL gz = FN(grid_row)(th + 8, xn, yn, zn);
                 REAL ix = FN(unnormalize)(gx, Wi), iy = FN(unnormalize)(gy, Hi), iz = FN(unnormalize)(gz, Di);
                 if (padding == 1) { ix = FN(clip)(ix, Wi); iy = FN(clip)(iy, Hi); iz = FN(clip)(iz, Di); }
                 const long po = ((long)d * Ho + h) * Wo + w;
@@ -307,9 +317,9 @@ int FN(oracle_affine_sample_bwd_input)(const float *grad_out, const float *theta
             for (int h = 0; h < Ho; ++h)
                 for (int w = 0; w < Wo; ++w) {
                     const REAL xn = FN(base_coord)(w, Wo), yn = FN(base_coord)(h, Ho), zn = FN(base_coord)(d, Do);
-                    REAL gx = (REAL)th[0] * xn + (REAL)th[1] * yn + (REAL)th[2] * zn + (REAL)th[3];
-                    REAL gy = (REAL)th[4] * xn + (REAL)th[5] * yn + (REAL)th[6] * zn + (REAL)th[7];
-                    REAL gz = (REAL)th[8] * xn + (REAL)th[9] * yn + (REAL)th[10] * zn + (REAL)th[11];
+                    REAL gx = FN(grid_row)(th + 0, xn, yn, zn);
+                    REAL gy = FN(grid_row)(th + 4, xn, yn, zn);
+                    REAL gz = FN(grid_row)(th + 8, xn, yn, zn);
                     REAL ix = FN(unnormalize)(gx, Wi), iy = FN(unnormalize)(gy, Hi), iz = FN(unnormalize)(gz, Di);
                     if (padding == 1) { ix = FN(clip)(ix, Wi); iy = FN(clip)(iy, Hi); iz = FN(clip)(iz, Di); }
                     const REAL fx = FLOORFN(ix), fy = FLOORFN(iy), fz = FLOORFN(iz);
@@ -420,9 +430,9 @@ int FN(oracle_label_argmax)(const float *onehot, const float *theta, long long *
             for (int h = 0; h < Ho; ++h)
                 for (int w = 0; w < Wo; ++w) {
                     const REAL xn = FN(base_coord)(w, Wo), yn = FN(base_coord)(h, Ho), zn = FN(base_coord)(d, Do);
-                    const REAL gx = (REAL)th[0] * xn + (REAL)th[1] * yn + (REAL)th[2] * zn + (REAL)th[3];
-                    const REAL gy = (REAL)th[4] * xn + (REAL)th[5] * yn + (REAL)th[6] * zn + (REAL)th[7];
-                    const REAL gz = (REAL)th[8] * xn + (REAL)th[9] * yn + (REAL)th[10] * zn + (REAL)th[11];
+                    const REAL gx = FN(grid_row)(th + 0, xn, yn, zn);
+                    const REAL gy = FN(grid_row)(th + 4, xn, yn, zn);
+                    const REAL gz = FN(grid_row)(th + 8, xn, yn, zn);
                     const REAL rx = NEARBY(FN(unnormalize)(gx, Wi)), ry = NEARBY(FN(unnormalize)(gy, Hi)),
                                rz = NEARBY(FN(unnormalize)(gz, Di));
                     long long label = 0;

@@ -326,10 +326,44 @@ def gen_consistency():
     save("argmaxed_segs", segs=seg, out=ref_tu.get_argmaxed_segs(seg))
 
 
+def gen_nearest_ties():
+    """Index work must be bit-exact: label crops whose source coordinates sit exactly on .5 ties (a centre crop of an
+    odd-sized patch out of an even-sized volume maps every voxel to k + 0.5 on that axis), random crops, an up-sampling
+    crop, and general affines in nearest mode on a larger grid — all through the reference's get_batch
+    (torch_utils.py:13-82) / F.affine_grid + F.grid_sample(mode="nearest")."""
+    g = torch.Generator().manual_seed(1234)
+    vol = volume((1, 1, 14, 18, 22), 906)[0, 0]
+    ids = torch.randint(0, 6, (4, 5, 6), generator=g)                       # blocky label map, 0 = unlabeled
+    ids = ids.repeat_interleave(4, 0)[:14].repeat_interleave(4, 1)[:, :18].repeat_interleave(4, 2)[:, :, :22]
+    lab = torch.stack([(ids == l).float() for l in range(1, 6)])
+    sample = torch.cat([vol[None], lab], 0)
+    arrays = dict(sample=sample)
+    cases = [("tie_center", [7, 9, 11], "center", None), ("rand_a", [7, 9, 11], None, 61), ("rand_b", [6, 10, 12], None, 62),
+             ("up", [20, 18, 30], None, 63), ("same", [14, 18, 22], "center", None)]
+    for name, patch, fixed, seed in cases:
+        if seed is not None:
+            torch.manual_seed(seed)
+        b_img, b_lbl = ref_tu.get_batch([sample], [0, 0], patch, fixed_patch_idx=fixed, device="cpu")
+        arrays[f"{name}_patch"] = np.array(patch)
+        arrays[f"{name}_seed"] = np.array(-1 if seed is None else seed)
+        for i in range(2):
+            arrays[f"{name}_img{i}"] = b_img[i]
+            arrays[f"{name}_lbl{i}"] = b_lbl[i]
+    torch.manual_seed(64)
+    theta = torch.eye(3, 4).unsqueeze(0).repeat(3, 1, 1) + 0.15 * torch.randn(3, 3, 4)
+    theta[2] = torch.tensor([[0.5, 0, 0, 0.0], [0, 0.5, 0, 0.0], [0, 0, 0.5, 0.0]])   # exact ties on the odd axes below
+    src = torch.arange(3 * 2 * 14 * 18 * 22, dtype=torch.float32).view(3, 2, 14, 18, 22)   # value == linear index
+    out_size = [3, 2, 7, 9, 11]
+    grid = F.affine_grid(theta, out_size, align_corners=False)
+    arrays.update(theta=theta, src_shape=np.array(src.shape), out_size=np.array(out_size),
+                  nearest_zeros=F.grid_sample(src, grid, mode="nearest", padding_mode="zeros", align_corners=False),
+                  nearest_border=F.grid_sample(src, grid, mode="nearest", padding_mode="border", align_corners=False))
+    save("nearest_ties", **arrays)
+
+
 if __name__ == "__main__":
-    gen_mind()
-    gen_gin()
-    gen_affine()
-    gen_consistency()
+    groups = dict(mind=gen_mind, gin=gen_gin, affine=gen_affine, consistency=gen_consistency, nearest=gen_nearest_ties)
+    for name in (sys.argv[1:] or list(groups)):
+        groups[name]()
     total = sum(p.stat().st_size for p in OUT.glob("*.npz"))
     print(f"total fixture bytes: {total}")

@@ -102,4 +102,4 @@ def test_label_argmax_against_the_c_oracle():
     R, _ = get_rand_affine(2, strength=0.15)
     got = affine_label_argmax(lab.cuda(), R, (12, 20, 9)).cpu().numpy()
     ref = cform.label_argmax(lab.numpy(), R.numpy(), (12, 20, 9))
-    assert (got != ref).mean() <= 0.002          # nearest-neighbour ties at .5 may round differently in 1e-7 coordinates
+    assert np.array_equal(got, ref)              # index work is bit-exact: kernel and oracle execute torch's coordinate arithmetic
