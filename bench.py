@@ -29,6 +29,8 @@ sys.path.insert(0, str(ROOT))
 SHAPE = (2, 1, 192, 192, 192)
 METRIC = "gin_mind_aug voxels/s (GIN + MIND-SSC input transform)"
 UNIT = "voxels/s"
+WORKLOAD = ("gin_mind_aug (GIN 4-layer random conv stack + blend + Frobenius renorm -> MIND-SSC delta=1 sigma=1 with the "
+            "N(0,1)*0.05 edge noise) on 2x1x192x192x192 fp32 per step (BASELINE.json configs[1] shape)")
 MIND_BYTES_PER_VOXEL_NOISE = 100   # 4 in + 48 noise in + 48 out (noise streamed from HBM)
 MIND_BYTES_PER_VOXEL_CLEAN = 52
 
@@ -194,13 +196,154 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "gin_mind_aug 2x1x192x192x192 fp32 (BASELINE.json configs[1] shape), CPU sample = first "
-                               f"{depth} of 192 D-planes per step", "seeds": "torch.manual_seed(step)"},
+        "config": {"workload": WORKLOAD, "sample": f"CPU sample = first {depth} of 192 D-planes per step",
+                   "seeds": "torch.manual_seed(step)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"2x1x{depth}x192x192 slab, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def bind_rank_to_cores(local_rank, world):
+    """Give each rank its own slice of the host cores (and, through first touch, of the host memory the pinned buffers
+    land in).  Returns the core list, or None when there is nothing to split or the platform refuses."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity") or os.environ.get("DGTTA_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except OSError:
+        return None
+
+
+def gpu_eager_baseline(xs, dev, reps=3):
+    """The reference's own op sequence (torch eager: pad/conv3d chains, grouped convs; oracle/ref_port.py issues the same
+    ATen ops) on the SAME GPU with TF32 off — the kernel-vs-kernel bar of SURVEY.md §2b / BASELINE.md §4.  A reported
+    baseline like cpu_baseline: the product path never runs this."""
+    import torch
+    from oracle import ref_port
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        def draws(seed, b=SHAPE[0]):
+            torch.manual_seed(seed)
+            alphas = torch.rand(b, device=dev)
+            kers, shifts, cin = [], [], 1
+            for layer in range(4):
+                k = [1, 3][int(torch.randint(high=2, size=(1,))[0])]
+                cout = 1 if layer == 3 else 2
+                kers.append(torch.randn([cout * b, cin, k, k, k]).to(dev))
+                shifts.append(torch.randn([cout * b, 1, 1, 1]).to(dev))
+                cin = cout
+            return alphas, kers, shifts
+
+        def step(i):
+            alphas, kers, shifts = draws(i)
+            with torch.no_grad():
+                y = ref_port.gin(xs[i % len(xs)], kers, shifts, alphas)
+                return ref_port.mind_ssc(y, noise=torch.randn((SHAPE[0], 12) + SHAPE[2:], device=dev))
+
+        step(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            step(1 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        torch.cuda.empty_cache()
+        return {"value": SHAPE[0] * SHAPE[2] * SHAPE[3] * SHAPE[4] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": reps,
+                "kind": "torch eager on the same GPU (oracle/ref_port.py: the reference's ATen op sequence), TF32 off",
+                "seeds": "torch.manual_seed(step)"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def tta_record(rank, world, dev, steps=8, warmup=2):
+    """Second half of BASELINE.json's metric: inner steps/s of the stand-in TTA loop (dg_tta_b200/tta/standin.py), one
+    231x228x242 volume per GPU, patch 128^3, batch 2, PlainConvUNet-shaped fixture 12 -> 105 classes (14 optimised), with
+    the pre-network transform segment (crops, two view warps, two Philox fields, two MIND descriptors) replayed from one
+    CUDA graph.  Returns this rank's (ms per step, transform ms per step, launches, loss)."""
+    import torch
+    from dg_tta_b200 import _lib
+    from dg_tta_b200.tta import standin as ts
+    patch, batch = [128, 128, 128], 2
+    vol = synth_volume((1, 1, 231, 228, 242), 5000 + rank)[0].to(dev)
+    tr = ts.DropInTransforms()
+    torch.manual_seed(rank)
+    model = ts.StandInUNet(12, 105).to(dev)          # no hooks: MIND runs inside the graph
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    idx = list(range(1, 15))
+    views = ts.ViewGraph(vol, patch, batch)
+    torch.manual_seed(1000 + rank)
+
+    def step(i):
+        loss = ts.tta_inner_step_graphed(model, views, idx, tr)
+        if (i + 1) % 16 == 0:
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = _lib.lib().dgtta_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        loss = step(i)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    launches = _lib.lib().dgtta_launch_count() - launches0
+    # the transform segment alone (graph replays back to back)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        views.step()
+    g1.record()
+    torch.cuda.synchronize()
+    tms = g0.elapsed_time(g1) / steps
+    lossv = float(loss)
+    del model, opt, views
+    torch.cuda.empty_cache()
+    return ms, tms, int(launches), lossv
+
+
+def copy_ceiling(h_in, h_out, dev, steps, sync_all):
+    """Bare pinned-memory copies of the e2e leg's bytes (H2D of the input batch, D2H of a descriptor-sized buffer) on two
+    streams, all ranks at once, no kernels: the host-side ceiling the e2e number can be compared with."""
+    import torch
+    d_in = torch.empty_like(h_in[0], device=dev)
+    d_out = torch.empty(h_out[0].shape, dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def once(i):
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in[i % 2], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out[i % 2].copy_(d_out, non_blocking=True)
+
+    once(0)
+    sync_all()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    main = torch.cuda.current_stream(dev)
+    s_in.wait_stream(main)
+    s_out.wait_stream(main)
+    for i in range(steps):
+        once(i)
+    main.wait_stream(s_in)
+    main.wait_stream(s_out)
+    c1.record()
+    sync_all()
+    return c0.elapsed_time(c1) / steps
 
 
 def run_ours(args, rank, world, local_rank):
@@ -211,10 +354,13 @@ def run_ours(args, rank, world, local_rank):
     from dg_tta_b200.mind import mind_ssc
     from dg_tta_b200.tta.augmentation_utils import gin_mind_aug
 
+    from dg_tta_b200 import replicas
+
     _lib.lib()  # fail loudly right away if the CUDA library is missing
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     vox_step = SHAPE[0] * SHAPE[2] * SHAPE[3] * SHAPE[4]
+    affinity = bind_rank_to_cores(local_rank, world)   # before any pinned allocation: first-touch places the pages
 
     # three distinct input batches, rotated; every step also writes a fresh 679 MB descriptor -> the working set
     # per step (57 MB in + 679 MB noise + 679 MB out) is far larger than the 126 MB L2
@@ -332,13 +478,32 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = u0.elapsed_time(u1)
     sampler.recording = False
     sampler.stop_flag = True
+    ceiling_ms = copy_ceiling(h_in, h_out, dev, e2e_steps, sync_all)
+    del h_in, h_out, pipe
+    _lib.release_scratch()
+    torch.cuda.empty_cache()
 
-    times = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(times[0]), float(times[1])
+    # ---- second half of the metric: stand-in TTA inner steps/s (every rank adapts its own volume)
+    tta_ms = tta_tms = tta_launches = tta_loss = None
+    if not os.environ.get("DGTTA_BENCH_NO_TTA"):
+        sync_all()
+        tta_ms, tta_tms, tta_launches, tta_loss = tta_record(rank, world, dev)
+
+    # slowest rank decides (dg_tta_b200/replicas.py: all-reduce MAX over NCCL)
+    ms = replicas.max_over_ranks(ms, dev)
+    e2e_ms = replicas.max_over_ranks(e2e_ms, dev)
+    ceiling_ms = replicas.max_over_ranks(ceiling_ms, dev)
+    if tta_ms is not None:
+        tta_ms = replicas.max_over_ranks(tta_ms, dev)
+        tta_tms = replicas.max_over_ranks(tta_tms, dev)
     if rank != 0:
         return
+    eager = None
+    if not os.environ.get("DGTTA_BENCH_NO_EAGER"):
+        try:
+            eager = gpu_eager_baseline(xs, dev)
+        except Exception as exc:   # a reported baseline must not take the product's line down with it
+            eager = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -362,17 +527,27 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "gin_mind_aug (GIN 4-layer random conv stack + blend + Frobenius renorm -> MIND-SSC delta=1 "
-                               "sigma=1 with the torch.randn edge noise regenerated by the library's Philox kernel) on 2x1x192x192x192 fp32 per GPU (BASELINE.json "
-                               "configs[1] shape)",
+        "config": {"workload": WORKLOAD,
+                   "noise": "the torch.randn edge-noise field is regenerated bit-identically by the library's Philox kernel",
                    "l2": "3 rotating input batches; per-step working set 1.4 GB >> 126 MB L2",
                    "queue": "at most 4 steps in flight (host waits on the event of step i-4)",
                    "seeds": "torch.manual_seed(step) -> GIN kernel sizes/weights identical to the reference arm",
                    "parallelism": f"{world} independent replicas, one batch per GPU, no collective"},
         "e2e": {"value": vox_step * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": h_out[0].numel() * 4,
+                "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 12 * xs[0].numel() * 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "dg_tta_b200.host_pipeline.HostPipeline.submit (H2D / transform / D2H of consecutive steps overlapped)"},
+                "api": "dg_tta_b200.host_pipeline.HostPipeline.submit (H2D / transform / D2H of consecutive steps overlapped)",
+                # bare pinned copies of the same bytes on all ranks at once (no kernels): what the host side can move
+                "copy_ceiling_ms_per_step": ceiling_ms, "frac_of_copy_ceiling": ceiling_ms / (e2e_ms / e2e_steps),
+                "host_affinity": f"{len(affinity)} cores per rank" if affinity else "unbound"},
+        "tta": None if tta_ms is None else {
+            "metric": "TTA inner steps/s (stand-in loop, dg_tta_b200/tta/standin.py)", "value": world * 1e3 / tta_ms,
+            "unit": "steps/s", "n_gpus": world, "ms_per_step": tta_ms, "transform_ms_per_step": tta_tms, "steps": 8, "warmup": 2,
+            "gpu_launches": tta_launches, "loss": tta_loss,
+            "workload": "get_batch -> 2 x (affine view warp, MIND-SSC with Philox noise) in ONE CUDA graph -> PlainConvUNet-shaped "
+                        "fixture 12->105 ch (PyTorch/cuDNN, out of scope) -> channel select 14 -> inverse warp -> fused soft-Dice "
+                        "consistency -> backward; patch 128^3, batch 2, one 231x228x242 volume per GPU (BASELINE configs[2]/[4])"},
+        "gpu_eager_baseline": eager,
         "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (counted inside the library)
         "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1, noise and image tiles staged by TMA> (+finalize, fix-up)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -388,61 +563,28 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_tta(args, rank, world, local_rank):
-    """BASELINE configs 3/5: TTA inner steps/s (one accumulation iteration of dg_tta/tta/tta.py:221-275 per step,
-    AdamW step every 16) on a stand-in PlainConvUNet-shaped network with random weights, patch 128^3, batch 2,
-    one synthetic MR-like volume per GPU.  The backbone is PyTorch/cuDNN and out of scope; the transforms are ours."""
-    import numpy as np
+    """--workload tta: only the TTA record (BASELINE configs 3/5), with the driver's --steps / --warmup."""
     import torch
     import torch.distributed as dist
-    sys.path.insert(0, str(ROOT / "tools"))
-    import tta_standin as ts
-    from dg_tta_b200 import _lib
+    from dg_tta_b200 import _lib, replicas
     _lib.lib()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    patch, batch = [128, 128, 128], 2
-    vol = [synth_volume((1, 1, 231, 228, 242), 5000 + rank)[0].to(dev)]
-    tr = ts.DropInTransforms()
-    model = ts.build_model(tr, num_classes=105, seed=rank).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
-    idx = list(range(1, 15))
-    rng = np.random.RandomState(rank)
-
-    def step(i):
-        loss = ts.tta_inner_step(model, vol, patch, batch, idx, tr, rng=rng)
-        if (i + 1) % 16 == 0:
-            opt.step()
-            opt.zero_grad(set_to_none=True)
-        return loss
-
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches0 = _lib.lib().dgtta_launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        loss = step(i)
-    t1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms, tms, launches, loss = tta_record(rank, world, dev, steps=args.steps, warmup=max(args.warmup, 2))
+    ms = replicas.max_over_ranks(ms, dev)
+    tms = replicas.max_over_ranks(tms, dev)
     if rank != 0:
         return
-    ms = float(ms[0])
     print(json.dumps({
-        "metric": "TTA inner steps/s (stand-in loop)", "value": world * args.steps / (ms * 1e-3), "unit": "steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "metric": "TTA inner steps/s (stand-in loop)", "value": world * 1e3 / ms, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "transform_ms_per_step": tms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "stand-in TTA inner step: get_batch -> 2x(affine warp, mind_hook -> PlainConvUNet-shaped "
-                               "fixture 12->105 ch, channel select 14, inverse warp) -> soft-Dice consistency -> backward; "
-                               "patch 128^3, batch 2, one 231x228x242 volume per GPU", "parallelism": f"{world} replicas"},
-        "gpu_launches": int(_lib.lib().dgtta_launch_count() - launches0), "loss": float(loss),
+        "config": {"workload": "stand-in TTA inner step: get_batch -> 2x(affine warp, MIND-SSC) in one CUDA graph -> "
+                               "PlainConvUNet-shaped fixture 12->105 ch, channel select 14, inverse warp -> soft-Dice consistency -> "
+                               "backward; patch 128^3, batch 2, one 231x228x242 volume per GPU", "parallelism": f"{world} replicas"},
+        "gpu_launches": launches, "loss": loss,
     }), flush=True)
 
 

@@ -26,6 +26,7 @@ SIGNATURES = {
     "dgtta_mind_philox_offset_increment": (c_uint64, [c_int] * 6),
     "dgtta_philox_normal_fill": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_int, c_int, c_void_p]),
     "dgtta_philox_normal_offset_increment": (c_uint64, [c_uint64, c_int, c_int]),
+    "dgtta_philox_normal_fill_graphsafe": (c_int, [c_void_p, c_uint64, c_void_p, c_int, c_int, c_void_p]),
     "dgtta_gin_workspace_bytes": (c_size_t, [c_int] * 7),
     "dgtta_gin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

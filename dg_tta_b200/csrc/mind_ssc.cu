@@ -14,7 +14,7 @@ using namespace dgtta;
 
 namespace dgtta {
 int philox_normal_fill(float *out, unsigned long long numel, unsigned long long seed, unsigned long long offset, int sms,
-                       int max_threads_per_sm, cudaStream_t stream);   // philox_normal.cu
+                       int max_threads_per_sm, cudaStream_t stream, const unsigned long long *state_dev = nullptr);   // philox_normal.cu
 }
 
 extern "C" size_t dgtta_mind_workspace_bytes(int B, int D, int H, int W)

@@ -53,9 +53,26 @@ __device__ __forceinline__ void one_call(float *__restrict__ out, unsigned numel
     if (!TAIL || li + 3u * T < numel) __stcs(out + li + 3u * T, b.y);
 }
 
+// state_dev == NULL: round keys and first counter are launch parameters.  state_dev != NULL (CUDA-graph mode): the
+// generator state {seed, offset} is read from device memory at run time — the way torch itself feeds Philox under
+// capture — so one captured launch draws a fresh field on every replay (the host updates the two words, e.g. through a
+// captured memcpy from pinned memory, and advances torch's generator by dgtta_philox_normal_offset_increment).
+template <bool DEV_STATE>
 __global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ out, unsigned numel, unsigned T,
-                                                            const __grid_constant__ Keys K, unsigned long long ctr0, int J)
+                                                            const __grid_constant__ Keys K0, unsigned long long ctr0_, int J,
+                                                            const unsigned long long *__restrict__ state_dev)
 {
+    Keys K = K0;   // DEV_STATE == false: never written, stays in the constant bank
+    unsigned long long ctr0 = ctr0_;
+    if (DEV_STATE) {
+        const unsigned long long seed = __ldg(state_dev), offset = __ldg(state_dev + 1);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            K.k[r][0] = (unsigned)seed + (unsigned)r * 0x9E3779B9u;
+            K.k[r][1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u;
+        }
+        ctr0 = offset >> 2;
+    }
     const unsigned idx = blockIdx.x * BLOCK + threadIdx.x;   // < T
     const int j0 = blockIdx.y * JB;
     if (j0 + JB < J) {
@@ -69,11 +86,11 @@ __global__ void __launch_bounds__(BLOCK) normal_fill_kernel(float *__restrict__ 
 
 }  // namespace philox
 
-void preload_philox() { DGTTA_TOUCH(philox::normal_fill_kernel); }
+void preload_philox() { DGTTA_TOUCH(philox::normal_fill_kernel<false>); DGTTA_TOUCH(philox::normal_fill_kernel<true>); }
 
 // shared with mind_ssc.cu (DGTTA_NOISE_PHILOX)
 int philox_normal_fill(float *out, unsigned long long numel, unsigned long long seed, unsigned long long offset, int sms,
-                       int max_threads_per_sm, cudaStream_t stream)
+                       int max_threads_per_sm, cudaStream_t stream, const unsigned long long *state_dev = nullptr)
 {
     if (numel == 0) return 0;
     if (!out) { set_error("dgtta_philox_normal_fill: null pointer"); return DGTTA_ENULL; }
@@ -95,7 +112,8 @@ int philox_normal_fill(float *out, unsigned long long numel, unsigned long long 
         K.k[r][0] = (unsigned)seed + (unsigned)r * 0x9E3779B9u;
         K.k[r][1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u;
     }
-    philox::normal_fill_kernel<<<grid, philox::BLOCK, 0, stream>>>(out, (unsigned)numel, (unsigned)T, K, offset / 4ull, J);
+    if (state_dev) philox::normal_fill_kernel<true><<<grid, philox::BLOCK, 0, stream>>>(out, (unsigned)numel, (unsigned)T, K, 0ull, J, state_dev);
+    else philox::normal_fill_kernel<false><<<grid, philox::BLOCK, 0, stream>>>(out, (unsigned)numel, (unsigned)T, K, offset / 4ull, J, nullptr);
     return check_launch("philox_normal_fill_kernel");
 }
 
@@ -106,6 +124,14 @@ extern "C" int dgtta_philox_normal_fill(float *out_dev, uint64_t numel, uint64_t
 {
     return dgtta::philox_normal_fill(out_dev, numel, philox_seed, philox_offset, sm_count, max_threads_per_sm,
                                      (cudaStream_t)stream);
+}
+
+extern "C" int dgtta_philox_normal_fill_graphsafe(float *out_dev, uint64_t numel, const uint64_t *seed_offset_dev, int sm_count,
+                                                  int max_threads_per_sm, dgtta_stream_t stream)
+{
+    if (!seed_offset_dev) { dgtta::set_error("dgtta_philox_normal_fill_graphsafe: null state"); return DGTTA_ENULL; }
+    return dgtta::philox_normal_fill(out_dev, numel, 0, 0, sm_count, max_threads_per_sm, (cudaStream_t)stream,
+                                     reinterpret_cast<const unsigned long long *>(seed_offset_dev));
 }
 
 extern "C" uint64_t dgtta_philox_normal_offset_increment(uint64_t numel, int sm_count, int max_threads_per_sm)

@@ -59,6 +59,9 @@ int dgtta_preload_kernels(void);
  *   in_scale_dev: NULL, or [B,2] floats (a_b, c_b): the kernel reads I = (img * a_b) * c_b — the
  *                 deferred Frobenius re-normalisation of GIN (gin.py:228) when GIN feeds MIND.
  *   taps_host [ntaps] Gaussian taps (mind.py:27-37), ntaps odd, 1..9
+ *   Output range: [0, 1].  The epilogue evaluates exp(-m/v) as ex2.approx.ftz(m * (-log2 e * rcp.approx.ftz(v))): results
+ *                 below 2^-126 flush to exactly 0 where the reference returns a denormal (both are < 1.2e-38; inside the
+ *                 1e-5 tolerance), and every voxel has at least one channel equal to 1.
  *   noise_mode/noise_dev/philox_*: see DGTTA_NOISE_*.  For PHILOX, noise_dev is a caller-owned scratch
  *                 of B*12*D*H*W floats that the call fills with the field torch.randn_like(edge_selection)
  *                 (mind.py:150) draws for the device generator state (seed, offset) before the draw
@@ -79,7 +82,12 @@ int dgtta_mind_ssc_fwd(const float *img_dev, float *out_dev, const float *in_sca
  * are the device properties torch uses. */
 uint64_t dgtta_mind_philox_offset_increment(int B, int D, int H, int W, int sm_count, int max_threads_per_sm);
 
-/* The N(0,1) field torch.randn(numel elements, device="cuda") writes for generator state (seed, offset):
+/* Host-side note (dg_tta_b200/mind.py): where torch's own launch split or a stream capture makes the stream
+ * irreproducible from host-known (seed, offset) — >= 2^31 elements, offset % 4 != 0, capture without the graph-safe
+ * entry below — the Python layer draws the field with torch.randn itself (the reference's own draw: identical values)
+ * and passes it as DGTTA_NOISE_TENSOR.  That is still this library's MIND kernel; only the noise generator is torch's.
+ *
+ * The N(0,1) field torch.randn(numel elements, device="cuda") writes for generator state (seed, offset):
  * Philox4x32-10 + Box-Muller in torch's element order (ATen/native/cuda/DistributionTemplates.h), the
  * draw behind mind.py:150.  offset must be a multiple of 4 and numel < 2^31 (torch's single-launch case);
  * sm_count / max_threads_per_sm are the device properties torch derives its grid from.
@@ -87,6 +95,12 @@ uint64_t dgtta_mind_philox_offset_increment(int B, int D, int H, int W, int sm_c
 int dgtta_philox_normal_fill(float *out_dev, uint64_t numel, uint64_t philox_seed, uint64_t philox_offset,
                              int sm_count, int max_threads_per_sm, dgtta_stream_t stream);
 uint64_t dgtta_philox_normal_offset_increment(uint64_t numel, int sm_count, int max_threads_per_sm);
+/* CUDA-graph form of the same fill: the generator state {seed, offset} (two uint64) is read from device memory when
+ * the kernel runs — as torch feeds Philox under capture — so one captured launch draws a fresh field per replay.  The
+ * caller rewrites the two words before each replay (a captured memcpy from pinned memory) and advances the
+ * generator by dgtta_philox_normal_offset_increment.  Same stream of values as dgtta_philox_normal_fill. */
+int dgtta_philox_normal_fill_graphsafe(float *out_dev, uint64_t numel, const uint64_t *seed_offset_dev, int sm_count,
+                                       int max_threads_per_sm, dgtta_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GIN augmentation.  Replaces GINGroupConv.forward (dg_tta/gin.py:168-230) and the per-layer

@@ -66,7 +66,8 @@ def shift_table():
 def mind_ssc(img, delta=1, sigma=1, randn_weighting=0.05, noise=None, precision="f32", taps=None):
     """MIND3D.forward (dg_tta/mind.py:142-164).  noise=None means randn_weighting is ignored
     (noise-free); otherwise `noise` is the tensor the reference would have drawn at mind.py:150."""
-    img = _f32(img)
+    # precision "f64x": double arithmetic AND a double input image (chain truth: GIN's f64 output is not rounded)
+    img = np.ascontiguousarray(img, dtype=np.float64) if precision == "f64x" else _f32(img)
     B, C, D, H, W = img.shape
     assert C == 1
     taps = gaussian_taps(sigma) if taps is None else _f32(taps)
@@ -78,7 +79,7 @@ def mind_ssc(img, delta=1, sigma=1, randn_weighting=0.05, noise=None, precision=
         assert nz.shape == out.shape
     fn = getattr(lib(), f"oracle_mind_ssc_{precision}")
     fn.restype = ctypes.c_int
-    rc = fn(_ptr(img), _ptr(nz) if nz is not None else None,
+    rc = fn(_ptr(img, ctypes.c_double if precision == "f64x" else ctypes.c_float), _ptr(nz) if nz is not None else None,
             _ptr(out, ctypes.c_float if precision == "f32" else ctypes.c_double),
             B, D, H, W, int(delta), _ptr(taps), len(taps), ctypes.c_float(randn_weighting))
     if rc:

@@ -45,3 +45,12 @@ void oracle_mind_shift_table(int *shift1, int *shift2)
 #define NEARBY nearbyint
 #define FMAFN fma
 #include "dgtta_oracle_impl.h"
+#undef REAL
+#undef SUFFIX
+
+/* chain truth: the same double-precision functions with a double-precision MIND input, so that GIN -> MIND can be
+ * evaluated without rounding the intermediate volume to float32 (oracle_mind_ssc_f64x) */
+#define REAL double
+#define SUFFIX _f64x
+#define IMGT double
+#include "dgtta_oracle_impl.h"

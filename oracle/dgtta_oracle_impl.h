@@ -17,6 +17,11 @@
 #error "include from dgtta_oracle.c"
 #endif
 
+#ifndef IMGT
+#define IMGT float /* element type of oracle_mind_ssc's input image; double only for the *_f64x chain-truth variant */
+#define IMGT_DEFAULTED
+#endif
+
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 #define FN(name) CAT(name, SUFFIX)
@@ -61,7 +66,7 @@ static void FN(smooth_axis)(const REAL *src, REAL *dst, long planes, int D, int 
     }
 }
 
-int FN(oracle_mind_ssc)(const float *img, const float *noise, REAL *out, int B, int D, int H, int W,
+int FN(oracle_mind_ssc)(const IMGT *img, const float *noise, REAL *out, int B, int D, int H, int W,
                         int delta, const float *taps_f, int ntaps, float randn_weighting)
 {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || delta < 1 || ntaps < 1 || !(ntaps & 1)) return 1;
@@ -78,7 +83,7 @@ int FN(oracle_mind_ssc)(const float *img, const float *noise, REAL *out, int B, 
 #pragma omp parallel for schedule(static)
     for (long bc = 0; bc < (long)B * 12; ++bc) {
         const int bi = (int)(bc / 12), c = (int)(bc % 12);
-        const float *I = img + bi * V;
+        const IMGT *I = img + bi * V;
         const int *s1 = MIND_SHIFT1[c], *s2 = MIND_SHIFT2[c];
         for (int d = 0; d < D; ++d)
             for (int h = 0; h < H; ++h)
@@ -454,6 +459,10 @@ int FN(oracle_label_argmax)(const float *onehot, const float *theta, long long *
     return 0;
 }
 
+#ifdef IMGT_DEFAULTED
+#undef IMGT
+#undef IMGT_DEFAULTED
+#endif
 #undef FN
 #undef CAT
 #undef CAT_

@@ -112,7 +112,7 @@ def test_full_size_properties(shape, delta):
     m = MIND3D(delta=delta)
     out = m(x, noise=False)
     assert torch.equal(out, m(x, noise=False))
-    assert bool((out.amax(1) == 1.0).all()) and bool((out > 0).all() | True) and bool((out <= 1).all())
+    assert bool((out.amax(1) == 1.0).all()) and bool((out >= 0).all()) and bool((out <= 1).all())
     assert not torch.isnan(out).any()
     # oracle on the whole volume is cheap in C (seconds)
     ref = cform.mind_ssc(x.cpu().numpy(), delta=delta, noise=None)
