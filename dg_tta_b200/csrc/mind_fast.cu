@@ -853,6 +853,15 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
+// developer knob: DGTTA_TMA_PROMO = 0 (none) / 1 (64 B) / 2 (128 B, default) / 3 (256 B) L2 promotion of the TMA boxes
+static CUtensorMapL2promotion l2_promotion()
+{
+    const char *e = getenv("DGTTA_TMA_PROMO");
+    const int v = e ? atoi(e) : 2;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
+
 // 4-D view (W, H, D, B*12) of the [B,12,D,H,W] noise tensor; box = one halo tile of all 12 channels of one plane
 static bool make_noise_map(Params &P)
 {
@@ -865,7 +874,7 @@ static bool make_noise_map(Params &P)
     const cuuint32_t box[4] = {Mode<NOISE_TMA>::EW, Mode<NOISE_TMA>::BOX_ROWS, 1, 12};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(&P.noise_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(P.noise), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -881,7 +890,7 @@ static bool make_img_map(Params &P)
     const cuuint32_t box[3] = {Mode<NOISE_TMA>::TWD, Geom<DELTA, NOISE_TMA>::TR, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(&P.img_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P.img), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
