@@ -1,0 +1,615 @@
+// GIN augmentation — sm_100a path for the reference's configuration (gin_aug, dg_tta/gin.py:233-241: IN_CHANNELS=1,
+// N_LAYER=4, INTERM_CHANNELS=2, kernel sizes drawn from {1,3}), ALL SAMPLES OF THE BATCH IN ONE LAUNCH and up to TWO
+// 3x3x3 layers per launch.
+//
+// The 4-layer stack (gin.py:94-113, 139-164) is a chain of m <= 4 3x3x3 convolutions with 1x1x1 ("pointwise") layers in
+// between.  One launch runs a SEGMENT
+//     [pro: pointwise layers]  ->  conv A  ->  [mid: pointwise layers]  ->  conv B  ->  [epi: pointwise layers,
+//                                                             and on the last segment the alpha blend (gin.py:197)
+//                                                             + sum-of-squares partials (gin.py:200-216)]
+// (conv A and mid are absent in a single-conv segment), so the whole stack is at most two launches, a 1x1x1 layer never
+// costs a pass over memory and the 2-channel intermediate between conv A and conv B never leaves shared memory.
+//
+// A CTA owns a 32 x 32 (H x W) output patch of one sample and marches along D.  Per input plane p:
+//   stage  cp.async of the (halo 2) input tile, zero-filled outside the volume (the zero padding of gin.py:105-107); pro
+//          layers applied in place to the in-volume cells;
+//   A      34 rows x 9 column quads of conv-A outputs: every thread scatters its 6-position input windows into three
+//          pending output planes held in registers, finishes plane p-1, applies shift / leaky-ReLU / mid layers and
+//          writes it — zero outside the volume, because conv B zero-pads ITS input — to the mid tile in shared memory;
+//   B      32 rows x 8 quads of conv-B outputs from the mid tile, same scatter scheme; finishes output plane p-2,
+//          epilogue, float4 store.
+// Arithmetic is packed fp32x2 with the PAIR RUNNING OVER CHANNELS, not over neighbouring voxels: a 2-output-channel
+// layer accumulates (out0, out1) of one voxel with  FFMA2 acc, x.F32 (scalar broadcast), (w_o0, w_o1) (uniform pair);
+// the 2 -> 1 layer accumulates the two input channels' partial sums with  FFMA2 acc, (x_c0, x_c1), (w_c0, w_c1).  No
+// register shuffling builds operand pairs: two-channel tiles are stored interleaved (one LDS.64 per voxel yields both
+// channels), one-channel tiles give scalars.  Weights are kernel parameters in order of use, indexed by the CTA's sample
+// (LDCU.64 c[0][UR + imm], one per four FFMA2): no weight registers, no shared-memory traffic for them, no H2D copy.
+#include "common.cuh"
+
+namespace dgtta {
+namespace gins {
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 lds64(const float *p) { return *reinterpret_cast<const u64 *>(p); }
+
+constexpr int TH = 32, TW = 32;
+constexpr int NTHR = 320;                         // 10 warps: 306 conv-A tasks, 256 conv-B tasks
+constexpr int PITCH1 = 38;                        // one-channel tile: row pitch in words, == 2 (mod 4), so that the 16 lanes of an
+                                                  // LDS.64 wavefront (two tile rows x 8 quads) cover 32 distinct banks
+constexpr int PITCH2 = 43;                        // two-channel (interleaved) tile: row pitch in voxels, odd; voxel column c sits
+                                                  // at c + 2 (c >> 4): lanes q and q + 4 of a row would otherwise share banks
+constexpr int RA = TH + 2, QA = 9;                // conv-A outputs: rows h0-1 .. h0+32, quads from column w0-1 (36 columns, 34 used)
+constexpr int RIN2 = TH + 4;                      // input tile rows of a double segment (h0-2 ..), columns w0-2 .. w0+35
+constexpr int RIN1 = TH + 2;                      // input tile rows of a single segment (h0-1 ..), columns w0-1 .. w0+32
+constexpr int MAXPW = 3;                          // pointwise layers in a pro / mid / epi chain
+constexpr int MAXB = 8;                           // samples per launch (kernel-parameter budget)
+constexpr int RED_SLOTS = 1024;
+
+struct alignas(16) Pointwise {       // y_o = act(sum_i w[o][i] x_i + shift[o]); channels padded to 2 with zero weights
+    float w[2][2];
+    float shift[2];
+    int act;
+    int pad_;
+};
+
+struct alignas(16) Conv {
+    // in order of use.  cout == 2: [cin][kh][kd][kw][cout] (pairs over the output channels); cout == 1 (cin == 2):
+    // [kh][kd][kw][cin] (pairs over the input channels).  Reference layout of ker is [cout][cin][kd][kh][kw] (gin.py:94).
+    float w[2 * 2 * 27];
+    float shift[2];
+    int act;               // leaky ReLU after the shift (every layer but the stack's last, gin.py:112-113)
+    int pad_;
+};
+
+struct alignas(16) SampleWeights {
+    Pointwise pro[MAXPW], mid[MAXPW], epi[MAXPW];
+    Conv A, B;
+};
+
+struct SegParams {
+    const float *in;       // [B][rc][D][H][W]
+    float *out;            // [B][oc][D][H][W]
+    const float *x0;       // last segment: the stack's input [B][1][D][H][W]
+    double *partials;      // last segment: [B][RED_SLOTS][2]
+    unsigned *counters;    // last segment: [B] CTAs of the sample that have added their partial sums (zeroed by the caller)
+    float *scale;          // last segment: [B][2] = {1/(||mixed_b||+1e-5), ||x_b||}, written by the sample's last CTA
+    const float *alphas;   // [B]
+    int D, H, W;
+    int nTH, nTW, nCD, chunkD;
+    int rc, oc;            // channels of in / out per sample
+    int n_pro, n_mid, n_epi;
+    int b0;                // first sample of this launch
+    alignas(16) SampleWeights s[MAXB];
+};
+
+__device__ __forceinline__ void apply_pointwise(const Pointwise &L, float &c0, float &c1)
+{
+    float y0 = fmaf(L.w[0][1], c1, L.w[0][0] * c0) + L.shift[0];
+    float y1 = fmaf(L.w[1][1], c1, L.w[1][0] * c0) + L.shift[1];
+    if (L.act) { y0 = y0 > 0.f ? y0 : y0 * 0.01f; y1 = y1 > 0.f ? y1 : y1 * 0.01f; }
+    c0 = y0; c1 = y1;
+}
+
+__device__ __forceinline__ void cp_async4_zfill(float *dst_smem, const float *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 4 : 0;     // src-size 0: the four destination bytes are zero-filled, src is not read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Tail of a last segment: the CTA adds its two sums of squares to a slot of the sample's partials; the CTA that finds
+// it was the sample's last one reduces the slots (fixed order) and writes the re-normalisation factors of gin.py:200-228,
+// scale[b] = {1 / (||mixed_b||_F + 1e-5), ||x_b||_F} — no separate reduction launch.
+__device__ __forceinline__ void finish_norms(const SegParams &P, int b, double s_in, double s_mix, double (*red)[NTHR / 32], int nthr)
+{
+    __shared__ int is_last;
+    const int tid = threadIdx.x;
+    s_in = warp_sum(s_in); s_mix = warp_sum(s_mix);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s_in; red[1][tid >> 5] = s_mix; }
+    __syncthreads();
+    double *part = P.partials + (size_t)b * RED_SLOTS * 2;
+    if (tid == 0) {
+        double a = 0.0, m = 0.0;
+        for (int i = 0; i < nthr / 32; ++i) { a += red[0][i]; m += red[1][i]; }
+        const int slot = blockIdx.x % RED_SLOTS;
+        atomicAdd(&part[2 * slot], a);
+        atomicAdd(&part[2 * slot + 1], m);
+        __threadfence();
+        is_last = atomicAdd(&P.counters[b], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a = 0.0, m = 0.0;
+    for (int i = tid; i < RED_SLOTS; i += nthr) {
+        a += __ldcg(&part[2 * i]);
+        m += __ldcg(&part[2 * i + 1]);
+    }
+    a = warp_sum(a); m = warp_sum(m);
+    __syncthreads();
+    if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = m; }
+    __syncthreads();
+    if (tid == 0) {
+        a = 0.0; m = 0.0;
+        for (int i = 0; i < nthr / 32; ++i) { a += red[0][i]; m += red[1][i]; }
+        const float in_frob = (float)sqrt(a), self_frob = (float)sqrt(m);
+        P.scale[2 * b] = __fdiv_rn(1.0f, self_frob + 1e-5f);
+        P.scale[2 * b + 1] = in_frob;
+    }
+}
+
+// ---- tile geometry.  C == 1: plain words, pitch PITCH1.  C == 2: interleaved (c0, c1) per voxel, pitch PITCH2 voxels,
+// voxel column c stored at column c + 2 (c >> 4).
+template <int C> __device__ __forceinline__ constexpr int tile_words(int rows) { return C == 1 ? rows * PITCH1 : rows * PITCH2 * 2; }
+template <int C> __device__ __forceinline__ int cell_word(int row, int col, int ch)
+{
+    return C == 1 ? row * PITCH1 + col : (row * PITCH2 + col + 2 * (col >> 4)) * 2 + ch;
+}
+// word offsets of a thread's 6-voxel window (tile row `row`, first column 4 q): voxels 0..3 at lo + j, 4..5 at hi + j
+template <int C> __device__ __forceinline__ void window_base(int row, int q, int &lo, int &hi)
+{
+    if (C == 1) { lo = hi = row * PITCH1 + 4 * q; }
+    else {
+        lo = (row * PITCH2 + 4 * q + 2 * (q >> 2)) * 2;
+        hi = (row * PITCH2 + 4 * q + 2 * ((q + 1) >> 2)) * 2;
+    }
+}
+
+// One input plane scattered into the three pending output planes of a 3x3x3 convolution: acc[0] is output plane p+1 (tap
+// kd = 0), acc[1] plane p (kd = 1), acc[2] plane p-1 (kd = 2, complete afterwards); acc[.][k] belongs to the thread's k-th
+// output voxel and holds (out0, out1) for CO == 2, (partial sum over c0, over c1) for CO == 1.
+template <int CI, int CO>
+__device__ __forceinline__ void scatter_plane(const float *tile, int lo, int hi, const Conv &K, u64 (&acc)[3][4])
+{
+    constexpr int ROW = CI == 1 ? PITCH1 : PITCH2 * 2;
+    static_assert(CO == 2 || CI == 2, "a 1 -> 1 3x3x3 layer does not occur in the (1, 4, 2) configuration");
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const float *rl = tile + lo + kh * ROW, *rh = tile + hi + kh * ROW;
+        if (CI == 1) {
+            float x[6];
+            unpk(lds64(rl), x[0], x[1]); unpk(lds64(rl + 2), x[2], x[3]); unpk(lds64(rh + 4), x[4], x[5]);
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float *wv = &K.w[((kh * 3 + kd) * 3 + kw) * 2];
+                    const u64 Wp = pk(wv[0], wv[1]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(pk(x[k + kw], x[k + kw]), Wp, acc[kd][k]);
+                }
+        } else {
+            u64 X[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) X[j] = lds64((j < 4 ? rl : rh) + 2 * j);
+            if (CO == 2) {
+#pragma unroll
+                for (int ic = 0; ic < 2; ++ic) {
+                    float x[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) { float a, b2; unpk(X[j], a, b2); x[j] = ic == 0 ? a : b2; }
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float *wv = &K.w[(((ic * 3 + kh) * 3 + kd) * 3 + kw) * 2];
+                            const u64 Wp = pk(wv[0], wv[1]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(pk(x[k + kw], x[k + kw]), Wp, acc[kd][k]);
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float *wv = &K.w[((kh * 3 + kd) * 3 + kw) * 2];
+                        const u64 Wp = pk(wv[0], wv[1]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(X[k + kw], Wp, acc[kd][k]);
+                    }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void rotate(u64 (&acc)[3][4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc[2][k] = acc[1][k]; acc[1][k] = acc[0][k]; acc[0][k] = 0ull; }
+}
+
+// finished plane of a thread: y[o][k].  CO == 2: the pair is (out0, out1); CO == 1: out0 = sum of the pair.
+template <int CO>
+__device__ __forceinline__ void finish(const u64 (&a)[4], float (&y)[2][4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        unpk(a[k], lo, hi);
+        if (CO == 2) { y[0][k] = lo; y[1][k] = hi; }
+        else { y[0][k] = lo + hi; y[1][k] = 0.f; }
+    }
+}
+
+// CIN: channels of the tile the segment's first conv reads (after the pro layers).  COUT: channels conv B produces.
+// The mid tile always has two channels (INTERM_CHANNELS).
+template <int CIN, int COUT, bool DOUBLE, bool LAST>
+__global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constant__ SegParams P)
+{
+    constexpr int HALO = DOUBLE ? 2 : 1;
+    constexpr int RIN = DOUBLE ? RIN2 : RIN1;                 // input tile rows
+    constexpr int CIN_W = DOUBLE ? TW + 6 : TW + 2;           // input tile columns that are read (38 / 34)
+    constexpr int IN_WORDS = tile_words<CIN>(RIN);
+    constexpr int MID_WORDS = tile_words<2>(RA);
+    constexpr int CB_IN = DOUBLE ? 2 : CIN;                   // channels conv B reads
+    __shared__ __align__(16) float tin[2][IN_WORDS];
+    __shared__ __align__(16) float tmid[DOUBLE ? MID_WORDS : 4];   // single buffer: written after barrier 1, read after barrier 2
+    __shared__ double red[2][NTHR / 32];
+    const int tid = threadIdx.x;
+    const int D = P.D, H = P.H, W = P.W;
+    const size_t HW = (size_t)H * W, V = (size_t)D * HW;
+    const int bl = blockIdx.y;                                 // sample within this launch
+    const int b = P.b0 + bl;
+    const SampleWeights &S = P.s[bl];
+    int bid = blockIdx.x;
+    const int cd = bid % P.nCD; bid /= P.nCD;
+    const int tw = bid % P.nTW; bid /= P.nTW;
+    const int th = bid;
+    const int h0 = th * TH, w0 = tw * TW;
+    const int d0 = cd * P.chunkD, d1 = min(D, d0 + P.chunkD);
+    const float *in = P.in + (size_t)b * P.rc * V;
+
+    // ---- conv-B task of this thread: output row ty, columns w0 + 4 tx ..
+    const bool b_task = tid < TH * 8;
+    const int ty = (tid >> 3) & (TH - 1), tx = tid & 7;
+    const int oh = h0 + ty, ow = w0 + 4 * tx;
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ok[k] = b_task && oh < H && (ow + k < W);
+    float *outp = P.out + (size_t)b * P.oc * V;
+    const bool vec_ok = ok[3] && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) &&
+                        (!LAST || (reinterpret_cast<uintptr_t>(P.x0) & 15) == 0);
+    int b_lo, b_hi;
+    window_base<CB_IN>(ty, tx, b_lo, b_hi);
+    // ---- conv-A task: 8 quads of every row first (conflict-free half-warps), then the ninth quad of every row
+    int ar = 0, aq = 0;
+    bool a_task = false;
+    if (DOUBLE) {
+        a_task = tid < RA * QA;
+        if (tid < RA * 8) { ar = tid >> 3; aq = tid & 7; }
+        else if (a_task) { ar = tid - RA * 8; aq = 8; }
+    }
+    int a_lo, a_hi;
+    window_base<CIN>(ar, aq, a_lo, a_hi);
+    const int a_gh = h0 - 1 + ar;                              // volume row of the conv-A output row
+    const bool a_row_in = a_gh >= 0 && a_gh < H;
+
+    u64 accA[3][4], accB[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accA[s][k] = accB[s][k] = 0ull;
+    double s_in = 0.0, s_mix = 0.0;
+    float alpha = 0.f;
+    if (LAST) alpha = __ldg(P.alphas + b);
+
+    // staging of input plane p into tin[buf]: every thread copies the same cells of every plane
+    auto stage = [&](int p, int buf) {
+        const bool plane_in = p >= 0 && p < D;
+        const float *src = in + (size_t)(plane_in ? p : 0) * HW;
+        for (int i = tid; i < RIN * CIN_W; i += NTHR) {
+            const int rr = i / CIN_W, cc = i - rr * CIN_W;
+            const int gh = h0 - HALO + rr, gw = w0 - HALO + cc;
+            const bool v = plane_in && gh >= 0 && gh < H && gw >= 0 && gw < W;
+            const size_t g = v ? (size_t)gh * W + gw : 0;
+            cp_async4_zfill(&tin[buf][cell_word<CIN>(rr, cc, 0)], src + g, v);
+            if (CIN > 1) {
+                if (P.rc > 1) cp_async4_zfill(&tin[buf][cell_word<CIN>(rr, cc, 1)], src + V + g, v);
+                else tin[buf][cell_word<CIN>(rr, cc, 1)] = 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+    // pro layers, in place, on this thread's own cells (visible to it after cp.async.wait_group), in-volume cells only:
+    // the zero padding of the conv applies to the pro layers' OUTPUT (gin.py:105-107)
+    auto prologue = [&](int p, int buf) {
+        if (P.n_pro == 0 || p < 0 || p >= D) return;
+        for (int i = tid; i < RIN * CIN_W; i += NTHR) {
+            const int rr = i / CIN_W, cc = i - rr * CIN_W;
+            const int gh = h0 - HALO + rr, gw = w0 - HALO + cc;
+            if (gh < 0 || gh >= H || gw < 0 || gw >= W) continue;
+            float *c = &tin[buf][cell_word<CIN>(rr, cc, 0)];
+            float c0 = c[0], c1 = CIN > 1 ? c[1] : 0.f;
+#pragma unroll
+            for (int l = 0; l < MAXPW; ++l)
+                if (l < P.n_pro) apply_pointwise(S.pro[l], c0, c1);
+            c[0] = c0;
+            if (CIN > 1) c[1] = c1;
+        }
+    };
+
+    // input planes p = d0 - HALO .. d1 - 1 + HALO.  DOUBLE: plane p completes conv-A plane p-1 and output plane p-2.
+    const int p_begin = d0 - HALO, p_end = d1 + HALO;
+    stage(p_begin, 0);
+    for (int p = p_begin; p < p_end; ++p) {
+        const int buf = (p - p_begin) & 1;
+        cp_async_wait_all();
+        prologue(p, buf);
+        __syncthreads();                                       // barrier 1: plane p staged by everyone; last turn's readers are done
+        if (p + 1 < p_end) stage(p + 1, buf ^ 1);
+        if (DOUBLE) {
+            // ================= conv A: input plane p -> pending planes; plane qa = p-1 complete
+            const int qa = p - 1;
+            if (a_task) {
+                if (p >= 0 && p < D) scatter_plane<CIN, 2>(tin[buf], a_lo, a_hi, S.A, accA);
+                float y[2][4];
+                finish<2>(accA[2], y);
+                const bool plane_in = qa >= 0 && qa < D && a_row_in;
+                float *m = &tmid[cell_word<2>(ar, 4 * aq, 0)];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int gw = w0 - 1 + 4 * aq + k;
+                    float c0 = y[0][k] + S.A.shift[0], c1 = y[1][k] + S.A.shift[1];      // gin.py:111
+                    if (S.A.act) { c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f; }
+#pragma unroll
+                    for (int l = 0; l < MAXPW; ++l)
+                        if (l < P.n_mid) apply_pointwise(S.mid[l], c0, c1);
+                    const bool v = plane_in && gw >= 0 && gw < W;                         // conv B zero-pads its input
+                    // the quad's four voxels are contiguous in the tile (4 aq .. 4 aq + 3 never straddles a multiple of 16)
+                    *reinterpret_cast<float2 *>(m + 2 * k) = make_float2(v ? c0 : 0.f, v ? c1 : 0.f);
+                }
+                rotate(accA);
+            }
+            __syncthreads();                                   // barrier 2: mid plane qa complete
+        }
+        // ================= conv B: its input plane qi (mid plane p-1, or input plane p) -> output plane qi-1 complete
+        const int qi = DOUBLE ? p - 1 : p;
+        const int q = qi - 1;
+        if (b_task) {
+            if (qi >= 0 && qi < D) scatter_plane<CB_IN, COUT>(DOUBLE ? tmid : tin[buf], b_lo, b_hi, S.B, accB);
+            if (q >= d0 && q < d1) {
+                float y[2][4];
+                finish<COUT>(accB[2], y);
+                const size_t off = (size_t)q * HW + (size_t)oh * W + ow;
+                float xin[4];
+                if (LAST) {
+                    const float *x0 = P.x0 + (size_t)b * V;
+                    if (vec_ok) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x0 + off));
+                        xin[0] = xv.x; xin[1] = xv.y; xin[2] = xv.z; xin[3] = xv.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) xin[k] = ok[k] ? __ldg(x0 + off + k) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float c0 = y[0][k] + S.B.shift[0], c1 = y[1][k] + S.B.shift[1];        // gin.py:111
+                    if (S.B.act) { c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f; }   // gin.py:112-113
+                    if (COUT == 1) c1 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < MAXPW; ++l)
+                        if (l < P.n_epi) apply_pointwise(S.epi[l], c0, c1);
+                    if (LAST) {
+                        c0 = __fadd_rn(__fmul_rn(alpha, c0), __fmul_rn(1.0f - alpha, xin[k]));   // gin.py:197
+                        if (ok[k]) { s_in += (double)xin[k] * xin[k]; s_mix += (double)c0 * c0; }
+                    }
+                    y[0][k] = c0; y[1][k] = c1;
+                }
+                if (vec_ok) {
+                    *reinterpret_cast<float4 *>(outp + off) = make_float4(y[0][0], y[0][1], y[0][2], y[0][3]);
+                    if (!LAST && P.oc > 1) *reinterpret_cast<float4 *>(outp + V + off) = make_float4(y[1][0], y[1][1], y[1][2], y[1][3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (ok[k]) {
+                            outp[off + k] = y[0][k];
+                            if (!LAST && P.oc > 1) outp[V + off + k] = y[1][k];
+                        }
+                }
+            }
+            rotate(accB);
+        }
+    }
+    if (LAST) finish_norms(P, b, s_in, s_mix, red, NTHR);
+}
+
+// stack without any 3x3x3 layer: one elementwise pass over all samples (the four pointwise layers are epi[0..2], pro[0])
+__global__ void __launch_bounds__(256) gin_pointwise_kernel(const __grid_constant__ SegParams P)
+{
+    __shared__ double red[2][NTHR / 32];
+    const size_t V = (size_t)P.D * P.H * P.W;
+    const int bl = blockIdx.y, b = P.b0 + bl;
+    const SampleWeights &S = P.s[bl];
+    const float alpha = __ldg(P.alphas + b);
+    const float *in = P.in + (size_t)b * V;
+    float *out = P.out + (size_t)b * V;
+    double s_in = 0.0, s_mix = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += stride) {
+        const float x = __ldg(in + i);
+        float c0 = x, c1 = 0.f;
+#pragma unroll
+        for (int l = 0; l < MAXPW; ++l) apply_pointwise(S.epi[l], c0, c1);
+        apply_pointwise(S.pro[0], c0, c1);
+        c0 = __fadd_rn(__fmul_rn(alpha, c0), __fmul_rn(1.0f - alpha, x));   // gin.py:197
+        s_in += (double)x * x; s_mix += (double)c0 * c0;
+        out[i] = c0;
+    }
+    finish_norms(P, b, s_in, s_mix, red, 256);
+}
+
+static void fill_pointwise(Pointwise &L, const float *ker, const float *shift, int cin, int cout, int act)
+{
+    for (int o = 0; o < 2; ++o) {
+        for (int i = 0; i < 2; ++i) L.w[o][i] = (o < cout && i < cin) ? ker[o * cin + i] : 0.f;
+        L.shift[o] = o < cout ? shift[o] : 0.f;
+    }
+    L.act = act;
+}
+
+static void fill_conv(Conv &K, const float *ker, const float *shift, int cin, int cout, int act)
+{
+    for (int i = 0; i < 2 * 2 * 27; ++i) K.w[i] = 0.f;
+    // reference layout ker[o][i][kd][kh][kw] -> order of use (see Conv)
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int kd = 0; kd < 3; ++kd)
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float v = ker[(((o * cin + i) * 3 + kd) * 3 + kh) * 3 + kw];
+                        if (cout == 2) K.w[((((i * 3 + kh) * 3 + kd) * 3 + kw) * 2) + o] = v;
+                        else K.w[(((kh * 3 + kd) * 3 + kw) * 2) + i] = v;
+                    }
+    K.shift[0] = shift[0];
+    K.shift[1] = cout > 1 ? shift[1] : 0.f;
+    K.act = act;
+    K.pad_ = 0;
+}
+
+template <int CIN, int COUT, bool DOUBLE>
+static void launch_variant(const SegParams &P, dim3 grid, bool last, cudaStream_t stream)
+{
+    if (last) gin_stack_kernel<CIN, COUT, DOUBLE, true><<<grid, NTHR, 0, stream>>>(P);
+    else gin_stack_kernel<CIN, COUT, DOUBLE, false><<<grid, NTHR, 0, stream>>>(P);
+}
+
+template <int CIN, int COUT, bool DOUBLE>
+static void touch_variant()
+{
+    DGTTA_TOUCH(gin_stack_kernel<CIN, COUT, DOUBLE, true>);
+    DGTTA_TOUCH(gin_stack_kernel<CIN, COUT, DOUBLE, false>);
+}
+
+}  // namespace gins
+
+void preload_gin_fused()
+{
+    using namespace gins;
+    touch_variant<1, 1, true>(); touch_variant<1, 2, true>(); touch_variant<2, 1, true>(); touch_variant<2, 2, true>();
+    touch_variant<1, 2, false>(); touch_variant<2, 1, false>(); touch_variant<2, 2, false>();
+    DGTTA_TOUCH(gin_pointwise_kernel);
+}
+
+// Runs the tuned path for cfg (1, 4, 2).  params_host layout as in dgtta_gin_fwd.  buf0: device buffer of B*2*V floats
+// (the only intermediate that reaches memory: between the two launches of a stack with three or four 3x3x3 layers).
+// partials: [B][RED_SLOTS][2] doubles and counters: [B] unsigned, both zeroed by the caller.  scale: [B][2], written by the
+// last launch (see finish_norms).
+int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_host, const int *ks, const float *alphas_dev,
+                     int B, int D, int H, int W, float *buf0, double *partials, unsigned *counters, float *scale,
+                     cudaStream_t stream)
+{
+    using namespace gins;
+    const int cins[4] = {1, 2, 2, 2}, couts[4] = {2, 2, 2, 1};
+    size_t koff[4], soff[4], off = 0;
+    for (int L = 0; L < 4; ++L) {
+        const int k3 = ks[L] * ks[L] * ks[L];
+        koff[L] = off; off += (size_t)couts[L] * B * cins[L] * k3;
+        soff[L] = off; off += (size_t)couts[L] * B;
+    }
+    int convs[4], nconv = 0;
+    for (int L = 0; L < 4; ++L) if (ks[L] == 3) convs[nconv++] = L;
+    auto ker = [&](int L, int b) { return params_host + koff[L] + (size_t)b * couts[L] * cins[L] * ks[L] * ks[L] * ks[L]; };
+    auto shf = [&](int L, int b) { return params_host + soff[L] + (size_t)b * couts[L]; };
+
+    // segments: pairs of consecutive 3x3x3 layers; an odd one out runs alone, first (so that the pair comes last)
+    struct Seg { int a, b_; };                 // layer indices of conv A (-1: single) and conv B
+    Seg segs[2];
+    int nseg = 0;
+    if (nconv == 1) segs[nseg++] = {-1, convs[0]};
+    else if (nconv == 2) segs[nseg++] = {convs[0], convs[1]};
+    else if (nconv == 3) { segs[nseg++] = {-1, convs[0]}; segs[nseg++] = {convs[1], convs[2]}; }
+    else if (nconv == 4) { segs[nseg++] = {convs[0], convs[1]}; segs[nseg++] = {convs[2], convs[3]}; }
+
+    SegParams P;
+    P.D = D; P.H = H; P.W = W;
+    P.x0 = x_dev; P.partials = partials; P.counters = counters; P.scale = scale; P.alphas = alphas_dev;
+    P.nTH = (H + TH - 1) / TH; P.nTW = (W + TW - 1) / TW;
+
+    for (int b0 = 0; b0 < B; b0 += MAXB) {
+        const int nb = B - b0 < MAXB ? B - b0 : MAXB;
+        P.b0 = b0;
+        if (nconv == 0) {
+            for (int bl = 0; bl < nb; ++bl) {
+                for (int L = 0; L < 3; ++L) fill_pointwise(P.s[bl].epi[L], ker(L, b0 + bl), shf(L, b0 + bl), cins[L], couts[L], 1);
+                fill_pointwise(P.s[bl].pro[0], ker(3, b0 + bl), shf(3, b0 + bl), cins[3], couts[3], 0);
+            }
+            P.in = x_dev; P.out = out_dev; P.rc = 1; P.oc = 1; P.n_pro = 0; P.n_mid = 0; P.n_epi = 4;
+            P.nCD = 1; P.chunkD = D;
+            const size_t V = (size_t)D * H * W;
+            size_t gx = (V + 255) / 256;
+            const size_t cap = (size_t)sm_count() * 8;
+            if (gx > cap) gx = cap;
+            gin_pointwise_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, stream>>>(P);
+            const int rc = check_launch("gin_pointwise_kernel");
+            if (rc) return rc;
+            continue;
+        }
+        const float *cur = x_dev;
+        int cur_c = 1;
+        for (int s = 0; s < nseg; ++s) {
+            const bool dbl = segs[s].a >= 0;
+            const int La = segs[s].a, Lb = segs[s].b_;
+            const int first_conv = dbl ? La : Lb;
+            const bool last_seg = s == nseg - 1;
+            const int pro_begin = s == 0 ? 0 : first_conv;            // later segments: the layers before were the previous epi
+            const int epi_end = last_seg ? 4 : (segs[s + 1].a >= 0 ? segs[s + 1].a : segs[s + 1].b_);
+            P.n_pro = first_conv - pro_begin;
+            P.n_mid = dbl ? Lb - La - 1 : 0;
+            P.n_epi = epi_end - Lb - 1;
+            for (int bl = 0; bl < nb; ++bl) {
+                SampleWeights &S = P.s[bl];
+                const int b = b0 + bl;
+                for (int i = 0; i < P.n_pro; ++i) { const int L = pro_begin + i; fill_pointwise(S.pro[i], ker(L, b), shf(L, b), cins[L], couts[L], 1); }
+                for (int i = 0; i < P.n_mid; ++i) { const int L = La + 1 + i; fill_pointwise(S.mid[i], ker(L, b), shf(L, b), cins[L], couts[L], 1); }
+                for (int i = 0; i < P.n_epi; ++i) { const int L = Lb + 1 + i; fill_pointwise(S.epi[i], ker(L, b), shf(L, b), cins[L], couts[L], L != 3); }
+                if (dbl) fill_conv(S.A, ker(La, b), shf(La, b), cins[La], couts[La], 1);
+                fill_conv(S.B, ker(Lb, b), shf(Lb, b), cins[Lb], couts[Lb], Lb != 3);
+            }
+            const int cin_tile = cins[first_conv];                    // channels the first conv of the segment reads
+            const int cout_b = couts[Lb];
+            P.rc = cur_c;
+            P.oc = last_seg ? 1 : couts[epi_end - 1];
+            P.in = cur;
+            P.out = last_seg ? out_dev : buf0;
+            // D chunks: about two waves of (2 CTAs per SM) while keeping the warm-up planes a small fraction of a chunk
+            const long base = (long)P.nTH * P.nTW * nb;
+            int ncd = (int)((4L * sm_count() + base - 1) / base);
+            const int max_chunks = (D + 15) / 16;
+            if (ncd > max_chunks) ncd = max_chunks;
+            if (ncd < 1) ncd = 1;
+            P.chunkD = (D + ncd - 1) / ncd;
+            P.nCD = (D + P.chunkD - 1) / P.chunkD;
+            const dim3 grid((unsigned)(P.nTH * P.nTW * P.nCD), (unsigned)nb);
+            const int code = (cin_tile - 1) * 2 + (cout_b - 1);
+            if (dbl) {
+                switch (code) {
+                    case 0: launch_variant<1, 1, true>(P, grid, last_seg, stream); break;
+                    case 1: launch_variant<1, 2, true>(P, grid, last_seg, stream); break;
+                    case 2: launch_variant<2, 1, true>(P, grid, last_seg, stream); break;
+                    default: launch_variant<2, 2, true>(P, grid, last_seg, stream); break;
+                }
+            } else {
+                switch (code) {
+                    case 0: set_error("gin: a 1 -> 1 3x3x3 layer cannot occur in the (1, 4, 2) configuration"); return DGTTA_EINVAL;
+                    case 1: launch_variant<1, 2, false>(P, grid, last_seg, stream); break;
+                    case 2: launch_variant<2, 1, false>(P, grid, last_seg, stream); break;
+                    default: launch_variant<2, 2, false>(P, grid, last_seg, stream); break;
+                }
+            }
+            const int rc = check_launch("gin_stack_kernel");
+            if (rc) return rc;
+            cur = P.out;
+            cur_c = P.oc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace dgtta
