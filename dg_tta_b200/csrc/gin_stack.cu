@@ -248,8 +248,11 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
     constexpr int IN_WORDS = tile_words<CIN>(RIN);
     constexpr int MID_WORDS = tile_words<2>(RA);
     constexpr int CB_IN = DOUBLE ? 2 : CIN;                   // channels conv B reads
-    __shared__ __align__(16) float tin[2][IN_WORDS];
-    __shared__ __align__(16) float tmid[DOUBLE ? MID_WORDS : 4];   // single buffer: written after barrier 1, read after barrier 2
+    // dynamic shared memory: input tile x 2 (cp.async double buffer), mid tile x 2 (conv A of this turn writes one while
+    // conv B reads the other: one barrier per plane)
+    extern __shared__ __align__(16) float smem_dyn[];
+    float (*tin)[IN_WORDS] = reinterpret_cast<float (*)[IN_WORDS]>(smem_dyn);
+    float (*tmid)[MID_WORDS] = reinterpret_cast<float (*)[MID_WORDS]>(smem_dyn + 2 * IN_WORDS);
     __shared__ double red[2][NTHR / 32];
     const int tid = threadIdx.x;
     const int D = P.D, H = P.H, W = P.W;
@@ -299,19 +302,33 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
     float alpha = 0.f;
     if (LAST) alpha = __ldg(P.alphas + b);
 
-    // staging of input plane p into tin[buf]: every thread copies the same cells of every plane
+    // staging of input plane p into tin[buf]: every thread copies the same cells of every plane; their tile word and
+    // in-plane offset (-1: outside the volume -> zero fill) are computed once
+    constexpr int NCELL = (RIN * CIN_W + NTHR - 1) / NTHR;
+    int cs[NCELL], cg[NCELL];
+#pragma unroll
+    for (int k = 0; k < NCELL; ++k) {
+        const int i = tid + k * NTHR;
+        cs[k] = -1; cg[k] = -1;
+        if (i < RIN * CIN_W) {
+            const int rr = i / CIN_W, cc = i - rr * CIN_W;
+            const int gh = h0 - HALO + rr, gw = w0 - HALO + cc;
+            cs[k] = cell_word<CIN>(rr, cc, 0);
+            if (gh >= 0 && gh < H && gw >= 0 && gw < W) cg[k] = gh * W + gw;
+        }
+    }
     auto stage = [&](int p, int buf) {
         const bool plane_in = p >= 0 && p < D;
         const float *src = in + (size_t)(plane_in ? p : 0) * HW;
-        for (int i = tid; i < RIN * CIN_W; i += NTHR) {
-            const int rr = i / CIN_W, cc = i - rr * CIN_W;
-            const int gh = h0 - HALO + rr, gw = w0 - HALO + cc;
-            const bool v = plane_in && gh >= 0 && gh < H && gw >= 0 && gw < W;
-            const size_t g = v ? (size_t)gh * W + gw : 0;
-            cp_async4_zfill(&tin[buf][cell_word<CIN>(rr, cc, 0)], src + g, v);
+#pragma unroll
+        for (int k = 0; k < NCELL; ++k) {
+            if (cs[k] < 0) continue;
+            const bool v = plane_in && cg[k] >= 0;
+            const int g = v ? cg[k] : 0;
+            cp_async4_zfill(&tin[buf][cs[k]], src + g, v);
             if (CIN > 1) {
-                if (P.rc > 1) cp_async4_zfill(&tin[buf][cell_word<CIN>(rr, cc, 1)], src + V + g, v);
-                else tin[buf][cell_word<CIN>(rr, cc, 1)] = 0.f;
+                if (P.rc > 1) cp_async4_zfill(&tin[buf][cs[k] + 1], src + V + g, v);
+                else tin[buf][cs[k] + 1] = 0.f;
             }
         }
         cp_async_commit();
@@ -320,11 +337,10 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
     // the zero padding of the conv applies to the pro layers' OUTPUT (gin.py:105-107)
     auto prologue = [&](int p, int buf) {
         if (P.n_pro == 0 || p < 0 || p >= D) return;
-        for (int i = tid; i < RIN * CIN_W; i += NTHR) {
-            const int rr = i / CIN_W, cc = i - rr * CIN_W;
-            const int gh = h0 - HALO + rr, gw = w0 - HALO + cc;
-            if (gh < 0 || gh >= H || gw < 0 || gw >= W) continue;
-            float *c = &tin[buf][cell_word<CIN>(rr, cc, 0)];
+#pragma unroll
+        for (int k = 0; k < NCELL; ++k) {
+            if (cs[k] < 0 || cg[k] < 0) continue;
+            float *c = &tin[buf][cs[k]];
             float c0 = c[0], c1 = CIN > 1 ? c[1] : 0.f;
 #pragma unroll
             for (int l = 0; l < MAXPW; ++l)
@@ -334,24 +350,29 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
         }
     };
 
-    // input planes p = d0 - HALO .. d1 - 1 + HALO.  DOUBLE: plane p completes conv-A plane p-1 and output plane p-2.
-    const int p_begin = d0 - HALO, p_end = d1 + HALO;
+    // Input planes p = d0 - HALO ..  Single segment: plane p completes output plane p-1.  Double segment: conv A turns
+    // plane p into mid plane p-1 (buffer p & 1) while conv B, in the same turn, consumes mid plane p-2 from the other
+    // buffer and completes output plane p-3 — one barrier per plane.
+    const int p_begin = d0 - HALO, p_last_in = d1 - 1 + HALO;            // last input plane anybody needs
+    const int p_end = DOUBLE ? d1 + 3 : d1 + 1;
     stage(p_begin, 0);
     for (int p = p_begin; p < p_end; ++p) {
         const int buf = (p - p_begin) & 1;
         cp_async_wait_all();
         prologue(p, buf);
-        __syncthreads();                                       // barrier 1: plane p staged by everyone; last turn's readers are done
-        if (p + 1 < p_end) stage(p + 1, buf ^ 1);
+        __syncthreads();                                       // plane p staged and last turn's mid plane written by everyone;
+                                                               // last turn's readers of the other buffers are done
+        if (p + 1 <= p_last_in) stage(p + 1, buf ^ 1);
+        else cp_async_commit();
         if (DOUBLE) {
-            // ================= conv A: input plane p -> pending planes; plane qa = p-1 complete
+            // ================= conv A: input plane p -> pending planes; mid plane qa = p-1 complete
             const int qa = p - 1;
-            if (a_task) {
+            if (a_task && p <= p_last_in) {
                 if (p >= 0 && p < D) scatter_plane<CIN, 2>(tin[buf], a_lo, a_hi, S.A, accA);
                 float y[2][4];
                 finish<2>(accA[2], y);
                 const bool plane_in = qa >= 0 && qa < D && a_row_in;
-                float *m = &tmid[cell_word<2>(ar, 4 * aq, 0)];
+                float *m = &tmid[p & 1][cell_word<2>(ar, 4 * aq, 0)];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int gw = w0 - 1 + 4 * aq + k;
@@ -366,13 +387,12 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
                 }
                 rotate(accA);
             }
-            __syncthreads();                                   // barrier 2: mid plane qa complete
         }
-        // ================= conv B: its input plane qi (mid plane p-1, or input plane p) -> output plane qi-1 complete
-        const int qi = DOUBLE ? p - 1 : p;
+        // ================= conv B: its input plane qi (mid plane p-2 from last turn, or input plane p) -> output plane qi-1
+        const int qi = DOUBLE ? p - 2 : p;
         const int q = qi - 1;
-        if (b_task) {
-            if (qi >= 0 && qi < D) scatter_plane<CB_IN, COUT>(DOUBLE ? tmid : tin[buf], b_lo, b_hi, S.B, accB);
+        if (b_task && qi >= d0 - 1) {
+            if (qi >= 0 && qi < D) scatter_plane<CB_IN, COUT>(DOUBLE ? tmid[(p - 1) & 1] : tin[buf], b_lo, b_hi, S.B, accB);
             if (q >= d0 && q < d1) {
                 float y[2][4];
                 finish<COUT>(accB[2], y);
@@ -473,11 +493,35 @@ static void fill_conv(Conv &K, const float *ker, const float *shift, int cin, in
     K.pad_ = 0;
 }
 
+template <int CIN, bool DOUBLE>
+constexpr size_t smem_bytes()
+{
+    return sizeof(float) * (size_t)(2 * (CIN == 1 ? (DOUBLE ? RIN2 : RIN1) * PITCH1 : (DOUBLE ? RIN2 : RIN1) * PITCH2 * 2) +
+                                    2 * (DOUBLE ? RA * PITCH2 * 2 : 4));
+}
+
+template <int CIN, int COUT, bool DOUBLE, bool LAST>
+static void launch_one(const SegParams &P, dim3 grid, cudaStream_t stream)
+{
+    constexpr size_t SMEM = smem_bytes<CIN, DOUBLE>();
+    if (SMEM > 48 * 1024) {
+        // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
+        static bool configured_on[64] = {false};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (!configured_on[dev]) {
+            cudaFuncSetAttribute(gin_stack_kernel<CIN, COUT, DOUBLE, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+            configured_on[dev] = true;
+        }
+    }
+    gin_stack_kernel<CIN, COUT, DOUBLE, LAST><<<grid, NTHR, SMEM, stream>>>(P);
+}
+
 template <int CIN, int COUT, bool DOUBLE>
 static void launch_variant(const SegParams &P, dim3 grid, bool last, cudaStream_t stream)
 {
-    if (last) gin_stack_kernel<CIN, COUT, DOUBLE, true><<<grid, NTHR, 0, stream>>>(P);
-    else gin_stack_kernel<CIN, COUT, DOUBLE, false><<<grid, NTHR, 0, stream>>>(P);
+    if (last) launch_one<CIN, COUT, DOUBLE, true>(P, grid, stream);
+    else launch_one<CIN, COUT, DOUBLE, false>(P, grid, stream);
 }
 
 template <int CIN, int COUT, bool DOUBLE>
@@ -578,12 +622,23 @@ int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_hos
             P.oc = last_seg ? 1 : couts[epi_end - 1];
             P.in = cur;
             P.out = last_seg ? out_dev : buf0;
-            // D chunks: about two waves of (2 CTAs per SM) while keeping the warm-up planes a small fraction of a chunk
+            // D chunks: two CTAs are resident per SM.  Choose the chunk count that minimises
+            //   waves * (planes marched per CTA = chunk + warm-up planes + fixed per-CTA cost):
+            // splitting D fills idle SMs, but every chunk re-marches its halo planes and a partly filled last wave costs
+            // as much as a full one.
             const long base = (long)P.nTH * P.nTW * nb;
-            int ncd = (int)((4L * sm_count() + base - 1) / base);
-            const int max_chunks = (D + 15) / 16;
-            if (ncd > max_chunks) ncd = max_chunks;
-            if (ncd < 1) ncd = 1;
+            const long slots = 2L * sm_count();
+            const int warm = dbl ? 5 : 2;
+            const int max_chunks = (D + 7) / 8;
+            long best_cost = -1;
+            int ncd = 1;
+            for (int c = 1; c <= max_chunks; ++c) {
+                const int chunk = (D + c - 1) / c;
+                const int n = (D + chunk - 1) / chunk;
+                const long waves = (base * n + slots - 1) / slots;
+                const long cost = waves * (chunk + warm + 2);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; ncd = c; }
+            }
             P.chunkD = (D + ncd - 1) / ncd;
             P.nCD = (D + P.chunkD - 1) / P.chunkD;
             const dim3 grid((unsigned)(P.nTH * P.nTW * P.nCD), (unsigned)nb);

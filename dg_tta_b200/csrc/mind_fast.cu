@@ -25,8 +25,8 @@
 // streamed in (x1.6 box over-read, mostly L2 hits) and 48 B/voxel out.
 //
 // Global clamp (mind.py:158-160): pass 1 assumes it inactive and records {sum v, min positive v, max v}
-// per (CTA, batch).  mind_fast_finalize reduces them to mean_all(v) and lists the (CTA, batch) units whose
-// range leaves [0.001*mean, 1000*mean]; pass 2 recomputes exactly those 4-plane units with the clamp.
+// per (CTA, batch).  Pass 2 (mind_fast_fix_kernel) reduces them to mean_all(v) in every CTA and recomputes exactly the
+// 4-plane units whose range leaves [0.001*mean, 1000*mean] with the clamp.  Two launches per call.
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "mind_internal.cuh"
@@ -712,58 +712,65 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const 
                                  P.stats + (size_t)blockIdx.x * P.nbatch);
 }
 
-// pass 2: persistent CTAs walk the list of (CTA, batch) units whose clamp is active
+// pass 2 (one launch, no separate reduction kernel): every CTA reduces the per-unit statistics to mean_all(v) -> clamp
+// bounds (same code on the same data in every CTA: identical bounds), then recomputes, with the clamp, exactly those
+// (CTA, batch) units of pass 1 whose range of v leaves [0.001*mean, 1000*mean].  Unit u belongs to CTA u % gridDim.x.
 template <int DELTA, int NOISE>
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_fix_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_fix_kernel(const __grid_constant__ Params P, int nunits,
+                                                                            double inv_count)
 {
     extern __shared__ __align__(128) float smem[];
     __shared__ float red[3][C_WARPS];
     __shared__ uint64_t full_bar[PB + 1];
     __shared__ uint64_t empty_bar[PB + 1];
     __shared__ uint64_t img_bar;
-    const int count = P.fix_hdr[0];
-    const float lo = P.fix_lohi[0], hi = P.fix_lohi[1];
-    for (int u = blockIdx.x; u < count; u += gridDim.x) {
-        const int unit = P.fix_hdr[1 + u];
-        const int cta = unit / P.nbatch, n = unit - cta * P.nbatch;
-        int b, h0, w0, d0, d1;
-        decode_cta(P, cta, b, h0, w0, d0, d1);
-        // batch n of pass 1 emitted planes d0 + PB*n - 2R .. + PB-1 (clipped to the chunk)
-        const int lo_d = max(d0, d0 + n * PB - 2 * R), hi_d = min(d1 - 1, d0 + n * PB - 2 * R + PB - 1);
-        if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, full_bar, empty_bar, &img_bar, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
-        __syncthreads();
-    }
-}
-
-// one CTA: mean_all(v) -> clamp bounds; compact list of units needing pass 2
-__global__ void __launch_bounds__(1024) mind_fast_finalize(const float4 *stats, int nunits, double inv_count, int *fix_hdr,
-                                                           float *fix_lohi)
-{
-    __shared__ double red[32];
+    __shared__ double dred[NTHREADS / 32];
     __shared__ float s_lo, s_hi, s_mean;
+    __shared__ int s_count;
+    __shared__ int s_list[64];
     const int tid = threadIdx.x;
     double s = 0.0;
-    for (int i = tid; i < nunits; i += 1024) s += (double)stats[i].x;
+    for (int i = tid; i < nunits; i += NTHREADS) s += (double)P.stats[i].x;
     s = warp_sum(s);
-    if ((tid & 31) == 0) red[tid >> 5] = s;
-    if (tid == 0) fix_hdr[0] = 0;
+    if ((tid & 31) == 0) dred[tid >> 5] = s;
+    if (tid == 0) s_count = 0;
     __syncthreads();
     if (tid == 0) {
         double tot = 0.0;
-        for (int i = 0; i < 32; ++i) tot += red[i];
+        for (int i = 0; i < NTHREADS / 32; ++i) tot += dred[i];
         const float mean = (float)(tot * inv_count);
         s_mean = mean;
         s_lo = mean * 0.001f;   // mind.py:158-160
         s_hi = mean * 1000.f;
-        fix_lohi[0] = s_lo; fix_lohi[1] = s_hi;
     }
     __syncthreads();
     const float lo = s_lo, hi = s_hi, mean = s_mean;
-    for (int i = tid; i < nunits; i += 1024) {
-        const float4 st = stats[i];
-        // units that emitted nothing carry {0, inf, 0}
-        const bool touched = st.z > 0.f || st.y < __int_as_float(0x7f800000) || !(mean > 0.f);
-        if (touched && (!(mean > 0.f) || st.z > hi || st.y < lo)) fix_hdr[1 + atomicAdd(&fix_hdr[0], 1)] = i;
+    // this CTA's units, 64 candidates at a time
+    for (int base = blockIdx.x; base < nunits; base += 64 * gridDim.x) {
+        if (tid < 64) {
+            const int i = base + tid * gridDim.x;
+            if (i < nunits) {
+                const float4 st = P.stats[i];
+                // units that emitted nothing carry {0, inf, 0}
+                const bool touched = st.z > 0.f || st.y < __int_as_float(0x7f800000) || !(mean > 0.f);
+                if (touched && (!(mean > 0.f) || st.z > hi || st.y < lo)) s_list[atomicAdd(&s_count, 1)] = i;
+            }
+        }
+        __syncthreads();
+        const int count = s_count;
+        for (int u = 0; u < count; ++u) {
+            const int unit = s_list[u];
+            const int cta = unit / P.nbatch, n = unit - cta * P.nbatch;
+            int b, h0, w0, d0, d1;
+            decode_cta(P, cta, b, h0, w0, d0, d1);
+            // batch n of pass 1 emitted planes d0 + PB*n - 2R .. + PB-1 (clipped to the chunk)
+            const int lo_d = max(d0, d0 + n * PB - 2 * R), hi_d = min(d1 - 1, d0 + n * PB - 2 * R + PB - 1);
+            if (lo_d <= hi_d) process<DELTA, NOISE, true>(P, smem, red, full_bar, empty_bar, &img_bar, b, h0, w0, lo_d, hi_d + 1, lo, hi, nullptr);
+            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
     }
 }
 
@@ -825,10 +832,8 @@ static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStrea
     mind_fast_kernel<DELTA, NOISE><<<plan.ncta, NTHREADS, G::SMEM, stream>>>(P);
     int rc = check_launch("mind_fast_kernel");
     if (rc) return rc;
-    mind_fast_finalize<<<1, 1024, 0, stream>>>(P.stats, nunits, 1.0 / ((double)P.B * P.D * P.H * P.W), hdr, lohi);
-    rc = check_launch("mind_fast_finalize");
-    if (rc) return rc;
-    mind_fast_fix_kernel<DELTA, NOISE><<<sm_count() * CTAS_PER_SM, NTHREADS, G::SMEM, stream>>>(P);
+    mind_fast_fix_kernel<DELTA, NOISE><<<sm_count() * CTAS_PER_SM, NTHREADS, G::SMEM, stream>>>(
+        P, nunits, 1.0 / ((double)P.B * P.D * P.H * P.W));
     return check_launch("mind_fast_fix_kernel");
 }
 
@@ -921,7 +926,6 @@ void preload_mind_fast()
     touch_fast<1, DGTTA_NOISE_TENSOR>(); touch_fast<2, DGTTA_NOISE_TENSOR>(); touch_fast<3, DGTTA_NOISE_TENSOR>();
     touch_fast<1, fast::NOISE_TMA>();
     if (fast::CTAS_PER_SM == 1) { touch_fast<fast::CTAS_PER_SM == 1 ? 2 : 1, fast::NOISE_TMA>(); touch_fast<fast::CTAS_PER_SM == 1 ? 3 : 1, fast::NOISE_TMA>(); }
-    DGTTA_TOUCH(fast::mind_fast_finalize);
 }
 
 bool mind_fast_supported(const MindArgs &a)
