@@ -41,6 +41,8 @@ SIGNATURES = {
     "dgtta_affine_label_gather": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "dgtta_affine_crop_shifted_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "dgtta_volume_min_workspace_bytes": (c_size_t, []),
+    "dgtta_resize_edge_workspace_bytes": (c_size_t, [c_int] * 8),
+    "dgtta_resize_edge": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "dgtta_volume_min": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -15,7 +15,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libdgtta_sm100.so"
 OBJ_DIR = PKG / "build"
-SOURCES = ["api.cu", "mind_ssc.cu", "mind_fast.cu", "mind_general.cu", "gin.cu", "gin_stack.cu", "affine_sample.cu", "philox_normal.cu", "consistency_loss.cu"]
+SOURCES = ["api.cu", "mind_ssc.cu", "mind_fast.cu", "mind_general.cu", "gin.cu", "gin_stack.cu", "affine_sample.cu", "philox_normal.cu", "consistency_loss.cu", "resize.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -43,6 +43,7 @@ void preload_gin_fused();
 void preload_sampler();
 void preload_philox();
 void preload_consistency();
+void preload_resize();
 }
 
 // CUDA loads kernels lazily, on their first launch (a few ms each).  GIN alone has 22 instantiations selected by the
@@ -56,6 +57,7 @@ extern "C" int dgtta_preload_kernels(void)
     dgtta::preload_sampler();
     dgtta::preload_philox();
     dgtta::preload_consistency();
+    dgtta::preload_resize();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

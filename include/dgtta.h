@@ -185,6 +185,19 @@ int dgtta_consistency_sums_fwd(const float *target_a_dev, const float *target_b_
 int dgtta_consistency_sums_bwd(const float *target_a_dev, const float *target_b_dev, const float *grad_sums_dev,
                                float *grad_a_dev, int B, int C, long long V, dgtta_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MultiRes low-resolution simulation.  Replaces the two skimage.transform.resize(x, shape, order, mode='edge',
+ * anti_aliasing=False) calls per channel of augment_discrete_linear_downsampling_scipy
+ * (dg_tta/pretraining/discrete_downsampling.py:29-33; installed by nnUNetTrainer_GIN_MIND_MultiRes.py:57-69 with
+ * order_downsample = 0, order_upsample = 3).  skimage delegates to scipy.ndimage.zoom(..., mode='nearest',
+ * grid_mode=True) and clips to the input's range; orders 0 (nearest), 1 (linear) and 3 (cubic B-spline with the
+ * 12-sample edge pre-padding and prefilter of scipy) are built.
+ *   in_dev [N,Di,Hi,Wi] -> out_dev [N,Do,Ho,Wo]; the N volumes share the geometry (channels of one sample).
+ *   workspace: dgtta_resize_edge_workspace_bytes(...) bytes, 256-byte aligned. */
+size_t dgtta_resize_edge_workspace_bytes(int N, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int order);
+int dgtta_resize_edge(const float *in_dev, float *out_dev, int N, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int order,
+                      void *workspace_dev, size_t workspace_bytes, dgtta_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
