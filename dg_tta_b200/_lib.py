@@ -36,6 +36,8 @@ SIGNATURES = {
     "dgtta_affine_sample_bwd_input": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "dgtta_consistency_sums_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "dgtta_consistency_sums_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
+    "dgtta_consistency_warp_sums_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "dgtta_consistency_warp_sums_bwd": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "dgtta_affine_label_argmax": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "dgtta_label_map_from_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "dgtta_affine_label_gather": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),

@@ -55,10 +55,12 @@ struct alignas(16) Pointwise {       // y_o = act(sum_i w[o][i] x_i + shift[o]);
     int pad_;
 };
 
+constexpr int WROW = 20;   // floats per (cin, kh) weight row: 3 kd x 3 kw pairs = 18, padded to five float4
 struct alignas(16) Conv {
-    // in order of use.  cout == 2: [cin][kh][kd][kw][cout] (pairs over the output channels); cout == 1 (cin == 2):
-    // [kh][kd][kw][cin] (pairs over the input channels).  Reference layout of ker is [cout][cin][kd][kh][kw] (gin.py:94).
-    float w[2 * 2 * 27];
+    // in order of use, one row of WROW floats per (cin, kh) — cout == 2: row [cin][kh] = [kd][kw][cout] (pairs over the
+    // output channels); cout == 1 (cin == 2): row [kh] = [kd][kw][cin] (pairs over the input channels).  Rows are read as
+    // float4 (LDCU.128).  Reference layout of ker is [cout][cin][kd][kh][kw] (gin.py:94).
+    float w[2 * 3 * WROW];
     float shift[2];
     int act;               // leaky ReLU after the shift (every layer but the stack's last, gin.py:112-113)
     int pad_;
@@ -163,6 +165,19 @@ template <int C> __device__ __forceinline__ void window_base(int row, int q, int
 // One input plane scattered into the three pending output planes of a 3x3x3 convolution: acc[0] is output plane p+1 (tap
 // kd = 0), acc[1] plane p (kd = 1), acc[2] plane p-1 (kd = 2, complete afterwards); acc[.][k] belongs to the thread's k-th
 // output voxel and holds (out0, out1) for CO == 2, (partial sum over c0, over c1) for CO == 1.
+// the nine (kd, kw) weight pairs of one (cin, kh) row as uniform values
+struct WRow {
+    float v[WROW];
+};
+__device__ __forceinline__ WRow load_wrow(const Conv &K, int row)
+{
+    WRow r;
+    const float4 *p = reinterpret_cast<const float4 *>(&K.w[row * WROW]);
+#pragma unroll
+    for (int i = 0; i < WROW / 4; ++i) { const float4 f = p[i]; r.v[4 * i] = f.x; r.v[4 * i + 1] = f.y; r.v[4 * i + 2] = f.z; r.v[4 * i + 3] = f.w; }
+    return r;
+}
+
 template <int CI, int CO>
 __device__ __forceinline__ void scatter_plane(const float *tile, int lo, int hi, const Conv &K, u64 (&acc)[3][4])
 {
@@ -174,11 +189,12 @@ __device__ __forceinline__ void scatter_plane(const float *tile, int lo, int hi,
         if (CI == 1) {
             float x[6];
             unpk(lds64(rl), x[0], x[1]); unpk(lds64(rl + 2), x[2], x[3]); unpk(lds64(rh + 4), x[4], x[5]);
+            const WRow wr = load_wrow(K, kh);
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const float *wv = &K.w[((kh * 3 + kd) * 3 + kw) * 2];
+                    const float *wv = &wr.v[(kd * 3 + kw) * 2];
                     const u64 Wp = pk(wv[0], wv[1]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(pk(x[k + kw], x[k + kw]), Wp, acc[kd][k]);
@@ -193,22 +209,24 @@ __device__ __forceinline__ void scatter_plane(const float *tile, int lo, int hi,
                     float x[6];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) { float a, b2; unpk(X[j], a, b2); x[j] = ic == 0 ? a : b2; }
+                    const WRow wr = load_wrow(K, ic * 3 + kh);
 #pragma unroll
                     for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
-                            const float *wv = &K.w[(((ic * 3 + kh) * 3 + kd) * 3 + kw) * 2];
+                            const float *wv = &wr.v[(kd * 3 + kw) * 2];
                             const u64 Wp = pk(wv[0], wv[1]);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(pk(x[k + kw], x[k + kw]), Wp, acc[kd][k]);
                         }
                 }
             } else {
+                const WRow wr = load_wrow(K, kh);
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
-                        const float *wv = &K.w[((kh * 3 + kd) * 3 + kw) * 2];
+                        const float *wv = &wr.v[(kd * 3 + kw) * 2];
                         const u64 Wp = pk(wv[0], wv[1]);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) acc[kd][k] = ffma2(X[k + kw], Wp, acc[kd][k]);
@@ -373,17 +391,23 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
                 finish<2>(accA[2], y);
                 const bool plane_in = qa >= 0 && qa < D && a_row_in;
                 float *m = &tmid[p & 1][cell_word<2>(ar, 4 * aq, 0)];
+                // conv A is never the stack's last layer: shift + leaky ReLU (gin.py:111-113), then the mid layers
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    y[0][k] += S.A.shift[0]; y[1][k] += S.A.shift[1];
+                    y[0][k] = y[0][k] > 0.f ? y[0][k] : y[0][k] * 0.01f;
+                    y[1][k] = y[1][k] > 0.f ? y[1][k] : y[1][k] * 0.01f;
+                }
+                for (int l = 0; l < P.n_mid; ++l) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) apply_pointwise(S.mid[l], y[0][k], y[1][k]);
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int gw = w0 - 1 + 4 * aq + k;
-                    float c0 = y[0][k] + S.A.shift[0], c1 = y[1][k] + S.A.shift[1];      // gin.py:111
-                    if (S.A.act) { c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f; }
-#pragma unroll
-                    for (int l = 0; l < MAXPW; ++l)
-                        if (l < P.n_mid) apply_pointwise(S.mid[l], c0, c1);
                     const bool v = plane_in && gw >= 0 && gw < W;                         // conv B zero-pads its input
                     // the quad's four voxels are contiguous in the tile (4 aq .. 4 aq + 3 never straddles a multiple of 16)
-                    *reinterpret_cast<float2 *>(m + 2 * k) = make_float2(v ? c0 : 0.f, v ? c1 : 0.f);
+                    *reinterpret_cast<float2 *>(m + 2 * k) = make_float2(v ? y[0][k] : 0.f, v ? y[1][k] : 0.f);
                 }
                 rotate(accA);
             }
@@ -410,17 +434,28 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float c0 = y[0][k] + S.B.shift[0], c1 = y[1][k] + S.B.shift[1];        // gin.py:111
-                    if (S.B.act) { c0 = c0 > 0.f ? c0 : c0 * 0.01f; c1 = c1 > 0.f ? c1 : c1 * 0.01f; }   // gin.py:112-113
-                    if (COUT == 1) c1 = 0.f;
+                    y[0][k] += S.B.shift[0]; y[1][k] += S.B.shift[1];                      // gin.py:111
+                    if (COUT == 1) y[1][k] = 0.f;
+                }
+                if (S.B.act) {                                                             // gin.py:112-113
 #pragma unroll
-                    for (int l = 0; l < MAXPW; ++l)
-                        if (l < P.n_epi) apply_pointwise(S.epi[l], c0, c1);
-                    if (LAST) {
-                        c0 = __fadd_rn(__fmul_rn(alpha, c0), __fmul_rn(1.0f - alpha, xin[k]));   // gin.py:197
-                        if (ok[k]) { s_in += (double)xin[k] * xin[k]; s_mix += (double)c0 * c0; }
+                    for (int k = 0; k < 4; ++k) {
+                        y[0][k] = y[0][k] > 0.f ? y[0][k] : y[0][k] * 0.01f;
+                        y[1][k] = y[1][k] > 0.f ? y[1][k] : y[1][k] * 0.01f;
                     }
-                    y[0][k] = c0; y[1][k] = c1;
+                }
+                for (int l = 0; l < P.n_epi; ++l) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) apply_pointwise(S.epi[l], y[0][k], y[1][k]);
+                }
+                if (LAST) {
+                    float q_in = 0.f, q_mix = 0.f;      // four squares per turn in fp32, then one double add each
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        y[0][k] = __fadd_rn(__fmul_rn(alpha, y[0][k]), __fmul_rn(1.0f - alpha, xin[k]));   // gin.py:197
+                        if (ok[k]) { q_in = fmaf(xin[k], xin[k], q_in); q_mix = fmaf(y[0][k], y[0][k], q_mix); }
+                    }
+                    s_in += (double)q_in; s_mix += (double)q_mix;
                 }
                 if (vec_ok) {
                     *reinterpret_cast<float4 *>(outp + off) = make_float4(y[0][0], y[0][1], y[0][2], y[0][3]);
@@ -476,7 +511,7 @@ static void fill_pointwise(Pointwise &L, const float *ker, const float *shift, i
 
 static void fill_conv(Conv &K, const float *ker, const float *shift, int cin, int cout, int act)
 {
-    for (int i = 0; i < 2 * 2 * 27; ++i) K.w[i] = 0.f;
+    for (int i = 0; i < 2 * 3 * WROW; ++i) K.w[i] = 0.f;
     // reference layout ker[o][i][kd][kh][kw] -> order of use (see Conv)
     for (int o = 0; o < cout; ++o)
         for (int i = 0; i < cin; ++i)
@@ -484,8 +519,8 @@ static void fill_conv(Conv &K, const float *ker, const float *shift, int cin, in
                 for (int kh = 0; kh < 3; ++kh)
                     for (int kw = 0; kw < 3; ++kw) {
                         const float v = ker[(((o * cin + i) * 3 + kd) * 3 + kh) * 3 + kw];
-                        if (cout == 2) K.w[((((i * 3 + kh) * 3 + kd) * 3 + kw) * 2) + o] = v;
-                        else K.w[(((kh * 3 + kd) * 3 + kw) * 2) + i] = v;
+                        if (cout == 2) K.w[(i * 3 + kh) * WROW + (kd * 3 + kw) * 2 + o] = v;
+                        else K.w[kh * WROW + (kd * 3 + kw) * 2 + i] = v;
                     }
     K.shift[0] = shift[0];
     K.shift[1] = cout > 1 ? shift[1] : 0.f;

@@ -73,14 +73,17 @@ def _reference_soft_dice(smp_a, smp_b):
     return soft_dice_loss(smp_a, smp_b)
 
 
-def calc_branch(model, imgs, optimized_idx, with_grad, transforms):
-    """tta.py:480-579 for spatial_aug_type='affine', do_spatial_aug_in='both', no intensity augmentation."""
+def calc_branch(model, imgs, optimized_idx, with_grad, transforms, warp_back=True):
+    """tta.py:480-579 for spatial_aug_type='affine', do_spatial_aug_in='both', no intensity augmentation.
+    warp_back=False returns (selected logits, R_inverse) for a consumer that fuses the inverse warp."""
     ctx = torch.enable_grad() if with_grad else torch.no_grad()
     with ctx:
         R, R_inverse = transforms.get_rand_affine(imgs.shape[0], flip=False)
         imgs_aug = transforms.warp(imgs, R, "border")                       # tta.py:549-551
         target = model(imgs_aug)                                            # pre-hooks: gin (off), mind
         target = target.transpose(0, 1)[optimized_idx].transpose(0, 1)      # map_label(..., "logits"), torch_utils.py:214-222
+        if not warp_back:
+            return target, R_inverse
         return transforms.warp(target, R_inverse, "zeros")                  # tta.py:573-575
 
 
@@ -101,9 +104,16 @@ def tta_inner_step(model, volumes, patch_size, batch_size, optimized_idx, transf
     with torch.no_grad():
         imgs, _ = transforms.get_batch(volumes, idx, patch_size, fixed_patch_idx=None, device=volumes[0].device)
     imgs = torch.cat(imgs, dim=0)
-    target_a = calc_branch(model, imgs, optimized_idx, True, transforms)     # have_grad_in = branch_a
-    target_b = calc_branch(model, imgs, optimized_idx, False, transforms)
-    loss = consistency(target_a, target_b, transforms)
+    fused = getattr(transforms, "consistency_loss_warped", None)
+    if fused is not None and len(optimized_idx) <= 16:
+        # drop-in: inverse warps + mask + softmaxes + Dice sums in one pass (and one for the gradient)
+        la, Ra_inv = calc_branch(model, imgs, optimized_idx, True, transforms, warp_back=False)    # have_grad_in = branch_a
+        lb, Rb_inv = calc_branch(model, imgs, optimized_idx, False, transforms, warp_back=False)
+        loss = fused(la, lb, Ra_inv, Rb_inv, 1)
+    else:
+        target_a = calc_branch(model, imgs, optimized_idx, True, transforms)
+        target_b = calc_branch(model, imgs, optimized_idx, False, transforms)
+        loss = consistency(target_a, target_b, transforms)
     (loss / accum).backward()
     return loss.detach()
 
@@ -111,7 +121,7 @@ def tta_inner_step(model, volumes, patch_size, batch_size, optimized_idx, transf
 class DropInTransforms:
     """The B200 drop-in (dg_tta_b200) behind the small interface the loop needs."""
 
-    def __init__(self):
+    def __init__(self, fused_warp=True):
         from .. import gin, mind, utils
         from . import augmentation_utils as au
         from . import torch_utils as tu
@@ -120,6 +130,8 @@ class DropInTransforms:
         self.get_rand_affine, self.get_batch = au.get_rand_affine, tu.get_batch
         self._sample = au.affine_grid_sample
         self.consistency_loss = tu.consistency_dice_loss
+        if fused_warp:
+            self.consistency_loss_warped = tu.consistency_dice_loss_warped
 
     def warp(self, x, theta, padding):
         return self._sample(x, theta, padding_mode=padding)
@@ -221,10 +233,16 @@ def tta_inner_step_graphed(model_no_hooks, views, optimized_idx, transforms, acc
     called on the descriptors directly (no mind_hook: MIND already ran inside the graph)."""
     desc_a, desc_b, R_a_inv, R_b_inv = views.step()
     sel = lambda t: t.transpose(0, 1)[optimized_idx].transpose(0, 1)
-    target_a = transforms.warp(sel(model_no_hooks(desc_a)), R_a_inv, "zeros")
+    fused = getattr(transforms, "consistency_loss_warped", None)
+    la = sel(model_no_hooks(desc_a))
     with torch.no_grad():
-        target_b = transforms.warp(sel(model_no_hooks(desc_b)), R_b_inv, "zeros")
-    loss = consistency(target_a, target_b, transforms)
+        lb = sel(model_no_hooks(desc_b))
+    if fused is not None and len(optimized_idx) <= 16:
+        loss = fused(la, lb, R_a_inv, R_b_inv, 1)
+    else:
+        with torch.no_grad():
+            target_b = transforms.warp(lb, R_b_inv, "zeros")
+        loss = consistency(transforms.warp(la, R_a_inv, "zeros"), target_b, transforms)
     (loss / accum).backward()
     return loss.detach()
 

@@ -179,3 +179,64 @@ def consistency_dice_loss(target_a, target_b, start_class=1):
     else:
         dice = nominator / denominator
     return 1 - dice[:, start_class:].mean()
+
+
+class _ConsistencyWarpSums(torch.autograd.Function):
+    """_ConsistencySums with the two inverse warps fused in (csrc/consistency_loss.cu, *_warp kernels): the inputs are the
+    un-warped logits and the inverse affines; differentiable w.r.t. either logit tensor."""
+
+    @staticmethod
+    def forward(ctx, logits_a, logits_b, theta_a, theta_b):
+        L = _lib.lib()
+        a, b = logits_a.contiguous(), logits_b.contiguous()
+        B, C, D, H, W = a.shape
+        with torch.cuda.device(a.device):
+            sums = torch.empty((B, C, 2), device=a.device, dtype=torch.float64)
+            _lib.check(L.dgtta_consistency_warp_sums_fwd(a.data_ptr(), b.data_ptr(), theta_a.data_ptr(), theta_b.data_ptr(),
+                                                         sums.data_ptr(), B, C, D, H, W, _lib.stream_ptr()),
+                       "dgtta_consistency_warp_sums_fwd")
+        ctx.save_for_backward(a, b, theta_a, theta_b)
+        return sums.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        a, b, theta_a, theta_b = ctx.saved_tensors
+        L = _lib.lib()
+        B, C, D, H, W = a.shape
+        g = grad_sums.contiguous().to(torch.float32)
+        grads = [None, None, None, None]
+        with torch.cuda.device(a.device):
+            for i, (x, y, tx, ty) in enumerate(((a, b, theta_a, theta_b), (b, a, theta_b, theta_a))):   # symmetric in the branches
+                if ctx.needs_input_grad[i]:
+                    gx = torch.empty_like(x)
+                    _lib.check(L.dgtta_consistency_warp_sums_bwd(x.data_ptr(), y.data_ptr(), tx.data_ptr(), ty.data_ptr(),
+                                                                 g.data_ptr(), gx.data_ptr(), B, C, D, H, W, _lib.stream_ptr()),
+                               "dgtta_consistency_warp_sums_bwd")
+                    grads[i] = gx
+        return tuple(grads)
+
+
+def consistency_dice_loss_warped(logits_a, logits_b, theta_a, theta_b, start_class=1):
+    """consistency_dice_loss(affine_grid_sample(logits_a, theta_a), affine_grid_sample(logits_b, theta_b), start_class)
+    — the inverse warps of dg_tta/tta/tta.py:571-575 and the loss of :263-269 — without materialising the warped logits.
+    theta_*: [B,3,4] inverse affines (host or device).  More than 16 channels fall back to warp + consistency_dice_loss
+    (still this library's kernels)."""
+    from .augmentation_utils import _theta_on
+    _lib.require_cuda_f32(logits_a, "logits_a")
+    _lib.require_cuda_f32(logits_b, "logits_b")
+    if logits_a.shape != logits_b.shape or logits_a.dim() != 5:
+        raise ValueError("consistency_dice_loss_warped expects two [B,C,D,H,W] tensors of the same shape")
+    B, C = logits_a.shape[:2]
+    if C > 16:
+        return consistency_dice_loss(affine_grid_sample(logits_a, theta_a), affine_grid_sample(logits_b, theta_b), start_class)
+    theta_a = _theta_on(logits_a.device, theta_a, B)
+    theta_b = _theta_on(logits_a.device, theta_b, B)
+    V = logits_a[0, 0].numel()
+    sums = _ConsistencyWarpSums.apply(logits_a, logits_b, theta_a, theta_b)
+    nominator = sums[..., 0] / V
+    denominator = 0.5 * sums[..., 1] / V
+    if denominator.sum() == 0.0:
+        dice = (nominator * 0.0) + 1.0
+    else:
+        dice = nominator / denominator
+    return 1 - dice[:, start_class:].mean()

@@ -185,6 +185,19 @@ int dgtta_consistency_sums_fwd(const float *target_a_dev, const float *target_b_
 int dgtta_consistency_sums_bwd(const float *target_a_dev, const float *target_b_dev, const float *grad_sums_dev,
                                float *grad_a_dev, int B, int C, long long V, dgtta_stream_t stream);
 
+/* The same reductions with the inverse warps of the two branches fused in (dg_tta/tta/tta.py:571-575 feeding :263-268):
+ *     target_x = grid_sample(logits_x, affine_grid(theta_x, size), zeros padding, align_corners=False),   x in {a, b}
+ * is evaluated per output voxel inside the reduction, so the warped logits are never written or re-read — forward or
+ * backward.  logits_*_dev [B,C,D,H,W], theta_*_dev [B,3,4] (the inverse affines R^-1), C <= 16 (otherwise warp with
+ * dgtta_affine_sample_fwd and call dgtta_consistency_sums_*).  bwd: grad_logits_a_dev [B,C,D,H,W] is overwritten with
+ * d loss / d logits_a (adjoint of branch a's trilinear gather applied to d loss / d target_a; float atomics). */
+int dgtta_consistency_warp_sums_fwd(const float *logits_a_dev, const float *logits_b_dev, const float *theta_a_dev,
+                                    const float *theta_b_dev, double *sums_dev, int B, int C, int D, int H, int W,
+                                    dgtta_stream_t stream);
+int dgtta_consistency_warp_sums_bwd(const float *logits_a_dev, const float *logits_b_dev, const float *theta_a_dev,
+                                    const float *theta_b_dev, const float *grad_sums_dev, float *grad_logits_a_dev, int B, int C,
+                                    int D, int H, int W, dgtta_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * MultiRes low-resolution simulation.  Replaces the two skimage.transform.resize(x, shape, order, mode='edge',
  * anti_aliasing=False) calls per channel of augment_discrete_linear_downsampling_scipy

@@ -103,3 +103,57 @@ def test_label_argmax_against_the_c_oracle():
     got = affine_label_argmax(lab.cuda(), R, (12, 20, 9)).cpu().numpy()
     ref = cform.label_argmax(lab.numpy(), R.numpy(), (12, 20, 9))
     assert np.array_equal(got, ref)              # index work is bit-exact: kernel and oracle execute torch's coordinate arithmetic
+
+
+def test_fused_inverse_warp_loss_matches_unfused_and_oracle():
+    """consistency_dice_loss_warped (inverse warps fused into the reductions, tta.py:571-575 + :263-269) against
+    (a) the unfused product path warp -> consistency_dice_loss and (b) the C oracle chain in double precision:
+    loss value and d loss / d logits_a (and, with the roles swapped, d loss / d logits_b)."""
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss, consistency_dice_loss_warped
+    from oracle import cform
+    g = torch.Generator().manual_seed(21)
+    B, C, shape = 2, 6, (18, 22, 40)
+    la = torch.randn((B, C) + shape, generator=g) * 2 + 0.4
+    lb = torch.randn((B, C) + shape, generator=g) * 2 + 0.4
+    torch.manual_seed(3)
+    _, Ra = get_rand_affine(B, strength=0.08)
+    _, Rb = get_rand_affine(B, strength=0.08)
+    a1 = la.cuda().requires_grad_(True)
+    b1 = lb.cuda().requires_grad_(True)
+    fused = consistency_dice_loss_warped(a1, b1, Ra, Rb)
+    fused.backward()
+    a2 = la.cuda().requires_grad_(True)
+    b2 = lb.cuda().requires_grad_(True)
+    unfused = consistency_dice_loss(affine_grid_sample(a2, Ra), affine_grid_sample(b2, Rb))
+    unfused.backward()
+    assert abs(fused.item() - unfused.item()) <= 2e-6
+    for got, ref in ((a1.grad, a2.grad), (b1.grad, b2.grad)):
+        scale = float(ref.abs().max())
+        assert scale > 0 and float((got - ref).abs().max()) <= 2e-5 * scale
+    # oracle chain: warp (f64) -> loss + gradient w.r.t. the warped logits (f64) -> adjoint warp (f64)
+    wa = cform.affine_sample(la.numpy(), Ra.numpy(), la.shape, precision="f64")
+    wb = cform.affine_sample(lb.numpy(), Rb.numpy(), lb.shape, precision="f64")
+    loss64, gwa = cform.consistency_loss(wa.astype(np.float32), wb.astype(np.float32), precision="f64")
+    ga = cform.affine_sample_bwd_input(gwa.astype(np.float32), Ra.numpy(), la.shape, precision="f64")
+    assert abs(fused.item() - loss64) <= 1e-5
+    assert np.abs(a1.grad.cpu().numpy() - ga).max() <= 1e-4 * np.abs(ga).max()
+
+
+def test_fused_inverse_warp_loss_shapes_and_fallback():
+    """ragged sizes (W not a multiple of 32, H not of 8), C = 14 (the bench's class subset) and the > 16-channel fallback"""
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss, consistency_dice_loss_warped
+    g = torch.Generator().manual_seed(5)
+    for C, shape in ((14, (9, 13, 37)), (3, (7, 8, 33)), (18, (6, 9, 20))):
+        la = (torch.randn((1, C) + shape, generator=g) + 0.3).cuda().requires_grad_(True)
+        lb = (torch.randn((1, C) + shape, generator=g) + 0.3).cuda()
+        torch.manual_seed(C)
+        _, Ra = get_rand_affine(1, strength=0.1)
+        _, Rb = get_rand_affine(1, strength=0.1)
+        f = consistency_dice_loss_warped(la, lb, Ra, Rb)
+        (ga_f,) = torch.autograd.grad(f, la)
+        u = consistency_dice_loss(affine_grid_sample(la, Ra), affine_grid_sample(lb, Rb))
+        (ga_u,) = torch.autograd.grad(u, la)
+        assert abs(f.item() - u.item()) <= 2e-6
+        assert float((ga_f - ga_u).abs().max()) <= 2e-5 * float(ga_u.abs().max())

@@ -111,6 +111,29 @@ def main():
                      ("closs_torch_fwd_bwd_2x14x128", lambda: torch.autograd.grad(chain(), ta))):
         med, best = timeit(fn)
         res[name] = dict(ms=med, best=best, gbs=ta.numel() * 4 * 5 / med / 1e6)   # read a,b twice + write grad: 5 passes
+    # the whole TTA epilogue (tta.py:571-575 + 263-269, forward + backward w.r.t. branch a): unfused product path
+    # (2 warps + fused sums + their backwards) vs the fused-warp kernels
+    from dg_tta_b200.tta.torch_utils import consistency_dice_loss_warped
+    la = torch.randn(2, 14, 128, 128, 128, device="cuda", requires_grad=True)
+    lb = torch.randn(2, 14, 128, 128, 128, device="cuda")
+    _, Rb_inv = get_rand_affine(2)
+    for name, fn in (("tta_epilogue_unfused_fwd_bwd_2x14x128", lambda: torch.autograd.grad(consistency_dice_loss(affine_grid_sample(la, Ri), affine_grid_sample(lb, Rb_inv)), la)),
+                     ("tta_epilogue_fused_fwd_bwd_2x14x128", lambda: torch.autograd.grad(consistency_dice_loss_warped(la, lb, Ri, Rb_inv), la))):
+        med, best = timeit(fn)
+        res[name] = dict(ms=med, best=best)
+    from dg_tta_b200.tta.torch_utils import get_batch
+    vol = synth_volume((1, 1, 231, 228, 242), 9)[0].cuda()
+    lab = torch.zeros(104, 231, 228, 242, device="cuda")
+    lab[3, 50:150, 40:160, 60:180] = 1
+    sample = torch.cat([vol, lab], 0)
+    get_batch([sample], [0, 0], [128, 128, 128], device="cuda")
+    med, best = timeit(lambda: get_batch([sample], [0, 0], [128, 128, 128], device="cuda"))
+    res["get_batch_2_crops_104_labels_231x228x242_to_128"] = dict(ms=med, best=best)
+    del sample, lab
+    from dg_tta_b200.pretraining import resize_edge
+    xr = synth_volume((1, 2, 128, 128, 128), 10)[0].cuda()
+    med, best = timeit(lambda: resize_edge(resize_edge(xr, (64, 32, 21), 0), (128, 128, 128), 3))
+    res["lowres_sim_2ch_128_down_64x32x21_up_cubic"] = dict(ms=med, best=best)
     # torch eager comparison for the sampler
     import torch.nn.functional as F
     Rd = R.cuda()
