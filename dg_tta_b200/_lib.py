@@ -94,7 +94,8 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-_scratch = {}
+_scratch = {}            # (device, stream, tag) -> tensor; insertion order = age
+_SCRATCH_MAX = 4         # buffers kept at most (each can be hundreds of MB: 679 MB for MIND's noise field at 2x192^3)
 
 
 def scratch(device, tag, numel):
@@ -102,20 +103,35 @@ def scratch(device, tag, numel):
     tag), for intermediates that never leave an operator: the 12-channel noise field of MIND is 679 MB at 2x192^3, and
     re-allocating it per call makes the caching allocator's pool depth — and with it cudaMalloc stalls on the host —
     depend on how far the host runs ahead of the GPU.  Reuse is ordered by the stream the buffer is keyed on.
-    release_scratch() drops the buffers."""
+
+    The cache is bounded: at most _SCRATCH_MAX buffers live (least recently used first out — a dead stream's buffer
+    cannot pile up), and a buffer more than twice as large as the request is dropped and re-allocated at the requested
+    size.  release_scratch() frees everything (e.g. before the nnU-Net backbone needs the memory)."""
     import torch
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream, tag)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < numel:
+    buf = _scratch.pop(key, None)
+    if buf is not None and (buf.numel() < numel or buf.numel() > 2 * max(numel, 1)):
         buf = None
-        _scratch.pop(key, None)
-        buf = _scratch[key] = torch.empty(numel, device=device, dtype=torch.float32)
+    if buf is None:
+        while len(_scratch) >= _SCRATCH_MAX:
+            _scratch.pop(next(iter(_scratch)))
+        buf = torch.empty(numel, device=device, dtype=torch.float32)
+    _scratch[key] = buf          # re-inserted: most recently used
     return buf[:numel]
 
 
 def release_scratch():
     _scratch.clear()
+
+
+def require_no_grad(t, name, what):
+    """MIND / GIN are forward-only here (the reference never back-propagates through them: inputs carry no gradient and
+    gin.py:57 asserts it for its weights).  Refuse loudly instead of silently detaching."""
+    import torch
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError(f"{what}: {name} requires grad, but this operator has no backward (the DG-TTA loops never need "
+                           "one: MIND/GIN run on inputs without gradient); call it under torch.no_grad() or detach the input")
 
 
 def require_cuda_f32(t, name):

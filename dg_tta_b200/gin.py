@@ -75,6 +75,7 @@ def gin_forward(x, kers, shifts, alphas, interm_channels, defer_scale=False):
     when defer_scale (the consumer applies out = (mixed*scale[:,0])*scale[:,1], gin.py:228)."""
     _lib.require_cuda_f32(x, "x_in")
     _lib.require_cuda_f32(alphas, "alphas")
+    _lib.require_no_grad(x, "x_in", "GINGroupConv")
     L = _lib.lib()
     x = x.contiguous()
     B, C, D, H, W = x.shape

@@ -27,15 +27,48 @@ def get_rand_affine(batch_size, strength=0.05, flip=False):
     return affine[:, :3], affine.inverse()[:, :3]
 
 
+class _PinnedRing:
+    """Small host-side staging ring for the per-call affines (48 bytes per sample).  Allocating a pinned tensor per call
+    (`.pin_memory()`) costs tens of microseconds — more than the 1-channel warp kernel itself — so the slots are
+    allocated once; a slot is reused only after the copy that read it has completed (one event per slot)."""
+    SLOTS, FLOATS = 64, 12 * 64
+
+    def __init__(self):
+        self.buf = torch.empty((self.SLOTS, self.FLOATS), dtype=torch.float32).pin_memory()
+        self.events = [None] * self.SLOTS
+        self.next = 0
+
+    def stage(self, theta, device):
+        n = theta.numel()
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        slot = self.buf[i, :n].view(theta.shape)
+        slot.copy_(theta)
+        out = slot.to(device=device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+        return out
+
+
+_RING = None
+
+
 def _theta_on(device, theta, B):
+    global _RING
     if tuple(theta.shape) != (B, 3, 4):
         raise ValueError(f"theta must have shape [{B},3,4], got {tuple(theta.shape)}")
     theta = theta.to(dtype=torch.float32)
-    if not theta.is_cuda:
-        # 96 bytes per sample: stage through pinned memory so the upload is a truly asynchronous copy
-        # (a pageable-source .to(device) synchronises the host with the stream)
-        theta = theta.contiguous().pin_memory()
-    return theta.to(device=device, non_blocking=True).contiguous()
+    if theta.is_cuda:
+        return theta.to(device=device).contiguous()
+    if theta.numel() > _PinnedRing.FLOATS or torch.cuda.is_current_stream_capturing():
+        return theta.contiguous().pin_memory().to(device=device, non_blocking=True)
+    if _RING is None:
+        _RING = _PinnedRing()
+    # 48 bytes per sample: staged through pinned memory so the upload is a truly asynchronous copy
+    return _RING.stage(theta.contiguous(), device)
 
 
 class _AffineSample(torch.autograd.Function):

@@ -121,7 +121,11 @@ def tta_inner_step(model, volumes, patch_size, batch_size, optimized_idx, transf
 class DropInTransforms:
     """The B200 drop-in (dg_tta_b200) behind the small interface the loop needs."""
 
-    def __init__(self, fused_warp=True):
+    def __init__(self, fused_warp=False):
+        # fused_warp: route the loss through consistency_dice_loss_warped (inverse warps inside the reductions, nothing
+        # materialised).  Measured on B200 (2x14x128^3, fwd+bwd): 2.81 ms vs 1.80 ms for warp -> consistency_dice_loss —
+        # holding all channels of both branches per voxel caps the latency-bound gather at 16 warps/SM — so the default
+        # is the unfused (faster) sequence; see profiles/experiments/README.md.
         from .. import gin, mind, utils
         from . import augmentation_utils as au
         from . import torch_utils as tu
