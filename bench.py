@@ -215,6 +215,7 @@ def bind_rank_to_cores(local_rank, world):
         per = max(1, len(cores) // world)
         mine = cores[local_rank * per:(local_rank + 1) * per] or cores
         os.sched_setaffinity(0, mine)
+        bind_rank_to_cores.all_cores = cores
         return mine
     except OSError:
         return None
@@ -544,7 +545,10 @@ def run_ours(args, rank, world, local_rank):
     achieved = MIND_BYTES_PER_VOXEL_NOISE * vox_step / (mind_kernel_ms * 1e-3) / 1e9
     traffic = committed_dram_traffic()
 
-    # CPU baseline: the torch-CPU port on a bounded slab of the same batch (~15 s of CPU work)
+    # CPU baseline: the torch-CPU port on a bounded slab of the same batch (~15 s of CPU work), on ALL host cores (the
+    # other ranks have finished; undo this rank's core binding)
+    if affinity and getattr(bind_rank_to_cores, "all_cores", None):
+        os.sched_setaffinity(0, bind_rank_to_cores.all_cores)
     torch.set_num_threads(os.cpu_count() or 1)
     xc = xs[0].cpu()
     depth = cpu_sample_depth(xc, budget_s=15.0)
