@@ -20,16 +20,30 @@ namespace closs {
 
 constexpr int THREADS = 256;
 
-template <int CMAX>
-__device__ __forceinline__ bool load_softmax(const float *a, const float *b, size_t V, size_t v, int C, float (&pa)[CMAX],
+// exp(x) for x <= 0 as ex2.approx(x * log2 e): two instructions instead of expf's ~10; relative error <= 2^-22, far inside
+// the loss tolerance (softmax probabilities; results below 2^-126 flush to 0)
+__device__ __forceinline__ float exp_neg(float x) { return ex2_approx(x * 1.4426950408889634f); }
+
+// EXACT: the channel count is the template parameter itself (no per-channel `c < C` predicates); otherwise CMAX is an
+// upper bound and C the run-time count.
+template <int CMAX, bool EXACT = false>
+__device__ __forceinline__ bool load_softmax(const float *a, const float *b, size_t V, size_t v, int C_, float (&pa)[CMAX],
                                              float (&pb)[CMAX])
 {
+    const int C = EXACT ? CMAX : C_;
     float sa = 0.f, sb = 0.f, ma = -__int_as_float(0x7f800000), mb = ma;
+    const float *qa = a + v, *qb = b + v;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
         if (c < C) {
-            pa[c] = __ldg(a + (size_t)c * V + v);
-            pb[c] = __ldg(b + (size_t)c * V + v);
+            pa[c] = __ldg(qa);
+            pb[c] = __ldg(qb);
+            qa += V; qb += V;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
             sa += pa[c]; sb += pb[c];
             ma = fmaxf(ma, pa[c]); mb = fmaxf(mb, pb[c]);
         }
@@ -39,7 +53,7 @@ __device__ __forceinline__ bool load_softmax(const float *a, const float *b, siz
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
         if (c < C) {
-            pa[c] = expf(pa[c] - ma); pb[c] = expf(pb[c] - mb);
+            pa[c] = exp_neg(pa[c] - ma); pb[c] = exp_neg(pb[c] - mb);
             ea += pa[c]; eb += pb[c];
         }
     }
@@ -96,7 +110,7 @@ __device__ __forceinline__ bool softmax_pair(int C, float (&pa)[CMAX], float (&p
     float ea = 0.f, eb = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        if (c < C) { pa[c] = expf(pa[c] - ma); pb[c] = expf(pb[c] - mb); ea += pa[c]; eb += pb[c]; }
+        if (c < C) { pa[c] = exp_neg(pa[c] - ma); pb[c] = exp_neg(pb[c] - mb); ea += pa[c]; eb += pb[c]; }
     }
     const float ia = 1.f / ea, ib = 1.f / eb;
 #pragma unroll
@@ -125,10 +139,11 @@ __device__ __forceinline__ float reduce_scatter32(float (&x)[32], int lane)
 
 // C <= 16: the 2C per-voxel contributions of a warp's 32 voxels are reduce-scattered every iteration, so a thread
 // carries ONE accumulator instead of 2C (64 -> ~50 registers, twice the resident warps; the pass is latency-bound).
-template <int CMAX>
+template <int CMAX, bool EXACT = false>
 __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 3 : 1) sums_kernel(const float *__restrict__ ta, const float *__restrict__ tb,
-                                                                          double *__restrict__ sums, int C, size_t V)
+                                                                          double *__restrict__ sums, int C_, size_t V)
 {
+    const int C = EXACT ? CMAX : C_;
     __shared__ float red[THREADS / 32][2 * CMAX];
     const int b = blockIdx.y;
     const float *a = ta + (size_t)b * C * V, *bb = tb + (size_t)b * C * V;
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 3 : 1) sums_kernel(const
         for (size_t v0 = (size_t)blockIdx.x * THREADS + (threadIdx.x & ~31); v0 < V; v0 += stride) {
             const size_t v = v0 + lane;
             float pa[CMAX], pb[CMAX], x[32];
-            const bool live = v < V && load_softmax<CMAX>(a, bb, V, v, C, pa, pb);
+            const bool live = v < V && load_softmax<CMAX, EXACT>(a, bb, V, v, C, pa, pb);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 if (c < CMAX && c < C && live) {
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 3 : 1) sums_kernel(const
         for (int c = 0; c < CMAX; ++c) accN[c] = accD[c] = 0.f;
         for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < V; v += (size_t)gridDim.x * THREADS) {
             float pa[CMAX], pb[CMAX];
-            if (!load_softmax<CMAX>(a, bb, V, v, C, pa, pb)) continue;
+            if (!load_softmax<CMAX, EXACT>(a, bb, V, v, C, pa, pb)) continue;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) {
                 if (c < C) {
@@ -186,11 +201,12 @@ __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 3 : 1) sums_kernel(const
     }
 }
 
-template <int CMAX>
+template <int CMAX, bool EXACT = false>
 __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 4 : 1) grad_kernel(const float *__restrict__ ta, const float *__restrict__ tb,
-                                                       const float *__restrict__ gsums, float *__restrict__ grad_a, int C,
+                                                       const float *__restrict__ gsums, float *__restrict__ grad_a, int C_,
                                                        size_t V)
 {
+    const int C = EXACT ? CMAX : C_;
     __shared__ float g[2 * CMAX];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < 2 * C; i += THREADS) g[i] = gsums[(size_t)b * 2 * C + i];
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, CMAX <= 16 ? 4 : 1) grad_kernel(const
     float *ga = grad_a + (size_t)b * C * V;
     for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < V; v += (size_t)gridDim.x * THREADS) {
         float pa[CMAX], pb[CMAX];
-        if (!load_softmax<CMAX>(a, bb, V, v, C, pa, pb)) {
+        if (!load_softmax<CMAX, EXACT>(a, bb, V, v, C, pa, pb)) {
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
                 if (c < C) ga[(size_t)c * V + v] = 0.f;
@@ -321,6 +337,26 @@ __global__ void __launch_bounds__(THREADS, 2) grad_warp_kernel(const __grid_cons
     }
 }
 
+// channel counts up to 16 (every class subset the TTA plans use) get kernels specialised for the exact count
+template <int C>
+static void launch_sums_exact(int want, dim3 grid, cudaStream_t st, const float *a, const float *b, double *sums, size_t V)
+{
+    if (want == C) sums_kernel<C, true><<<grid, THREADS, 0, st>>>(a, b, sums, C, V);
+    else if constexpr (C > 1) launch_sums_exact<C - 1>(want, grid, st, a, b, sums, V);
+}
+template <int C>
+static void launch_grad_exact(int want, dim3 grid, cudaStream_t st, const float *a, const float *b, const float *g, float *ga, size_t V)
+{
+    if (want == C) grad_kernel<C, true><<<grid, THREADS, 0, st>>>(a, b, g, ga, C, V);
+    else if constexpr (C > 1) launch_grad_exact<C - 1>(want, grid, st, a, b, g, ga, V);
+}
+template <int C>
+static void touch_exact()
+{
+    DGTTA_TOUCH(sums_kernel<C, true>); DGTTA_TOUCH(grad_kernel<C, true>);
+    if constexpr (C > 1) touch_exact<C - 1>();
+}
+
 static unsigned grid_x(size_t V)
 {
     const size_t want = (V + THREADS - 1) / THREADS;
@@ -332,8 +368,8 @@ static unsigned grid_x(size_t V)
 
 void preload_consistency()
 {
-    DGTTA_TOUCH(closs::sums_kernel<8>); DGTTA_TOUCH(closs::sums_kernel<16>); DGTTA_TOUCH(closs::sums_kernel<32>);
-    DGTTA_TOUCH(closs::grad_kernel<8>); DGTTA_TOUCH(closs::grad_kernel<16>); DGTTA_TOUCH(closs::grad_kernel<32>);
+    closs::touch_exact<16>();
+    DGTTA_TOUCH(closs::sums_kernel<32>); DGTTA_TOUCH(closs::grad_kernel<32>);
     DGTTA_TOUCH(closs::sums_warp_kernel<8>); DGTTA_TOUCH(closs::sums_warp_kernel<16>);
     DGTTA_TOUCH(closs::grad_warp_kernel<8>); DGTTA_TOUCH(closs::grad_warp_kernel<16>);
 }
@@ -359,8 +395,7 @@ extern "C" int dgtta_consistency_sums_fwd(const float *target_a_dev, const float
     cudaError_t e = cudaMemsetAsync(sums_dev, 0, (size_t)B * C * 2 * sizeof(double), stream);
     if (e != cudaSuccess) { set_error("dgtta_consistency_sums_fwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
     const dim3 grid(closs::grid_x((size_t)V), (unsigned)B);
-    if (C <= 8) closs::sums_kernel<8><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, sums_dev, C, (size_t)V);
-    else if (C <= 16) closs::sums_kernel<16><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, sums_dev, C, (size_t)V);
+    if (C <= 16) closs::launch_sums_exact<16>(C, grid, stream, target_a_dev, target_b_dev, sums_dev, (size_t)V);
     else if (C <= 32) closs::sums_kernel<32><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, sums_dev, C, (size_t)V);
     else closs::sums_kernel<128><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, sums_dev, C, (size_t)V);
     return check_launch("consistency_sums_kernel");
@@ -374,8 +409,7 @@ extern "C" int dgtta_consistency_sums_bwd(const float *target_a_dev, const float
     if (!grad_sums_dev) { set_error("dgtta_consistency_sums_bwd: null pointer"); return DGTTA_ENULL; }
     cudaStream_t stream = (cudaStream_t)stream_;
     const dim3 grid(closs::grid_x((size_t)V), (unsigned)B);
-    if (C <= 8) closs::grad_kernel<8><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, grad_sums_dev, grad_a_dev, C, (size_t)V);
-    else if (C <= 16) closs::grad_kernel<16><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, grad_sums_dev, grad_a_dev, C, (size_t)V);
+    if (C <= 16) closs::launch_grad_exact<16>(C, grid, stream, target_a_dev, target_b_dev, grad_sums_dev, grad_a_dev, (size_t)V);
     else if (C <= 32) closs::grad_kernel<32><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, grad_sums_dev, grad_a_dev, C, (size_t)V);
     else closs::grad_kernel<128><<<grid, closs::THREADS, 0, stream>>>(target_a_dev, target_b_dev, grad_sums_dev, grad_a_dev, C, (size_t)V);
     return check_launch("consistency_grad_kernel");

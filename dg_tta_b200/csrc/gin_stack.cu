@@ -91,7 +91,7 @@ __device__ __forceinline__ void apply_pointwise(const Pointwise &L, float &c0, f
 {
     float y0 = fmaf(L.w[0][1], c1, L.w[0][0] * c0) + L.shift[0];
     float y1 = fmaf(L.w[1][1], c1, L.w[1][0] * c0) + L.shift[1];
-    if (L.act) { y0 = y0 > 0.f ? y0 : y0 * 0.01f; y1 = y1 > 0.f ? y1 : y1 * 0.01f; }
+    if (L.act) { y0 = fmaxf(y0, y0 * 0.01f); y1 = fmaxf(y1, y1 * 0.01f); }   // leaky_relu(0.01): max(y, 0.01 y)
     c0 = y0; c1 = y1;
 }
 
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     y[0][k] += S.A.shift[0]; y[1][k] += S.A.shift[1];
-                    y[0][k] = y[0][k] > 0.f ? y[0][k] : y[0][k] * 0.01f;
-                    y[1][k] = y[1][k] > 0.f ? y[1][k] : y[1][k] * 0.01f;
+                    y[0][k] = fmaxf(y[0][k], y[0][k] * 0.01f);      // leaky_relu(0.01) = max(y, 0.01 y)
+                    y[1][k] = fmaxf(y[1][k], y[1][k] * 0.01f);
                 }
                 for (int l = 0; l < P.n_mid; ++l) {
 #pragma unroll
@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
                 if (S.B.act) {                                                             // gin.py:112-113
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        y[0][k] = y[0][k] > 0.f ? y[0][k] : y[0][k] * 0.01f;
-                        y[1][k] = y[1][k] > 0.f ? y[1][k] : y[1][k] * 0.01f;
+                        y[0][k] = fmaxf(y[0][k], y[0][k] * 0.01f);
+                        y[1][k] = fmaxf(y[1][k], y[1][k] * 0.01f);
                     }
                 }
                 for (int l = 0; l < P.n_epi; ++l) {
