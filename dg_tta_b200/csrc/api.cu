@@ -1,6 +1,8 @@
 // Error reporting and device queries shared by the C-ABI entry points.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dgtta {
@@ -21,15 +23,15 @@ unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_REL
 
 int sm_count()
 {
-    static int cached[64] = {0};
+    static std::atomic<int> cached[64];   // zero-initialised; concurrent first calls all store the same value
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached[dev];
+    return n;
 }
 
 }  // namespace dgtta

@@ -25,6 +25,7 @@
 // channels), one-channel tiles give scalars.  Weights are kernel parameters in order of use, indexed by the CTA's sample
 // (LDCU.64 c[0][UR + imm], one per four FFMA2): no weight registers, no shared-memory traffic for them, no H2D copy.
 #include "common.cuh"
+#include <atomic>
 
 namespace dgtta {
 namespace gins {
@@ -541,7 +542,7 @@ static void launch_one(const SegParams &P, dim3 grid, cudaStream_t stream)
     constexpr size_t SMEM = smem_bytes<CIN, DOUBLE>();
     if (SMEM > 48 * 1024) {
         // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
-        static bool configured_on[64] = {false};
+        static std::atomic<bool> configured_on[64];   // idempotent set-up: a race only repeats it
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
         if (!configured_on[dev]) {

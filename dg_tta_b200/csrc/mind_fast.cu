@@ -28,6 +28,7 @@
 // per (CTA, batch).  Pass 2 (mind_fast_fix_kernel) reduces them to mean_all(v) in every CTA and recomputes exactly the
 // 4-plane units whose range leaves [0.001*mean, 1000*mean] with the clamp.  Two launches per call.
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <atomic>
 
 #include "mind_internal.cuh"
 
@@ -812,10 +813,10 @@ static int launch(const Params &P0, const Plan &plan, void *workspace, cudaStrea
 {
     using G = Geom<DELTA, NOISE>;
     // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
-    static bool configured_on[64] = {false};
+    static std::atomic<bool> configured_on[64];   // idempotent set-up: a race only repeats it
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    bool &configured = configured_on[dev];
+    std::atomic<bool> &configured = configured_on[dev];
     if (!configured) {
         cudaFuncSetAttribute(mind_fast_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         cudaFuncSetAttribute(mind_fast_fix_kernel<DELTA, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
@@ -843,18 +844,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised exactly once, thread-safe (C++11)
+    static const EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        else
-            cudaGetLastError();
-    }
+            return (EncodeTiledFn)p;
+        cudaGetLastError();
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
 

@@ -9,6 +9,7 @@
 // mind.py:158-160 inactive and records per CTA {sum v, min positive v, max v}; pass 2 (FIX) reduces
 // those to mean_all(v) and recomputes only CTAs in which some v leaves [0.001*mean, 1000*mean].
 #include "mind_internal.cuh"
+#include <atomic>
 
 
 namespace dgtta {
@@ -306,10 +307,10 @@ static int mind_launch(const MindParams &P, int ntiles, cudaStream_t stream)
 {
     using G = MindGeom<R>;
     // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per (instantiation, device)
-    static bool configured_on[64] = {false};
+    static std::atomic<bool> configured_on[64];   // idempotent set-up: a race only repeats it
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    bool &configured = configured_on[dev];
+    std::atomic<bool> &configured = configured_on[dev];
     if (!configured) {
         cudaFuncSetAttribute(mind_general_kernel<R, false, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         cudaFuncSetAttribute(mind_general_kernel<R, true, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
