@@ -37,7 +37,7 @@ if ll.exists():
             f.write(f"{v:10.1f} us {100 * v / tot:5.1f}%  x{n[k]:3d}  avg {v / n[k]:8.1f} us  {k}\n")
     shutil.copy(ll, dst / ll.name)
 
-for rep, vox in ((f"{tag}_mind_noise", 2 * 192 ** 3), (f"{tag}_mind_clean", 2 * 192 ** 3), (f"{tag}_gin3333", 192 ** 3),
+for rep, vox in ((f"{tag}_mind_noise", 2 * 192 ** 3), (f"{tag}_mind_clean", 2 * 192 ** 3), (f"{tag}_gin3333", 2 * 192 ** 3),
                  (f"{tag}_sampler", 2 * 128 ** 3), (f"{tag}_philox", 2 * 12 * 192 ** 3), (f"{tag}_closs", 2 * 128 ** 3)):
     path = src / f"{rep}.ncu-rep"
     if not path.exists():
@@ -48,7 +48,18 @@ for rep, vox in ((f"{tag}_mind_noise", 2 * 192 ** 3), (f"{tag}_mind_clean", 2 * 
         f"# ncu --set full --clock-control none --import-source on  ({rep}); summarised by tools/ncu_summary.py\n" + out)
 
 for name in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_bench_tta.json", f"{tag}_kernel_times.txt",
-             f"{tag}_eager_vs_ours.json", f"{tag}_nvidia_smi.csv"):
+             f"{tag}_eager_vs_ours.json", f"{tag}_nvidia_smi.csv", f"{tag}_sanitizer_memcheck.log",
+             f"{tag}_sanitizer_memcheck_small.log", f"{tag}_sanitizer_racecheck.log"):
     if (src / name).exists():
         shutil.copy(src / name, dst / name)
+for name, to in (("chain_errors.json", f"{tag}_chain_errors.json"), ("tta_dice.json", f"{tag}_tta_dice.json")):
+    if (src / name).exists():
+        shutil.copy(src / name, dst / to)
+# per-phase split of the MIND capture (S1 / S2 / C between the kernel's BAR.SYNCs)
+rep = src / f"{tag}_mind_noise.ncu-rep"
+if rep.exists():
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_phases.py"), str(rep), str(2 * 192 ** 3), "6"],
+                         capture_output=True, text=True).stdout
+    (dst / f"{tag}_mind_noise_phases.txt").write_text(
+        f"# tools/ncu_phases.py on the same capture as {tag}_mind_noise_ncu_summary.txt: segments between BAR.SYNCs (1 = S1, 2 = S2, 3 = C)\n" + out)
 print(sorted(p.name for p in dst.iterdir()))
