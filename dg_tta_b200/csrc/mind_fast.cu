@@ -21,8 +21,17 @@
 //      LDS.64 + LDS.128 + LDS.64 in the 40-column tile) give 4 W-smoothed values; the D smoothing runs
 //      on a 4-slot register window (slots are compile-time because PB == taps - 1); min / mean over the 12
 //      channels by two xor-shuffles; exp; one STG.128 per channel (full 128-byte lines per warp).
-// Three __syncthreads per 4 planes; HBM traffic is 4 B/voxel in (+halo via L2), 48 B/voxel of noise when it is
-// streamed in (x1.6 box over-read, mostly L2 hits) and 48 B/voxel out.
+// Three __syncthreads per 4 planes; HBM traffic is 4 B/voxel in, 48 B/voxel of noise when it is streamed in (the
+// x1.6 box over-read is served by L2 as long as neighbouring CTAs march in step: ncu dram__bytes_read = 0.737 GB
+// = the algorithmic 0.736 GB on 2 x 192^3) and 48 B/voxel out.
+//
+// Volume faces (TMA mode).  The replicate padding of E^2 (mind.py:22) costs nothing extra: S1 computes only quads
+// inside the volume, S2 reads the clamped ROW (rows above the volume re-read row rT, rows below keep the registers of
+// row rB) and stage C replaces the two COLUMNS left of w = 0 / right of w = W-1 by the border column.  The passes act
+// on different axes, so padding one axis after smoothing another is bit-identical to padding E^2 first.  (Round 1
+// let the S1 task owning a border position write the replicated copies: patches on a face then ran 1.25x, corner
+// patches 1.55x longer than interior ones — the kernel's duration was the corner patches' — and their lag behind
+// the neighbours defeated the L2 sharing of the halo boxes: 1.07 GB read.)
 //
 // Global clamp (mind.py:158-160): pass 1 assumes it inactive and records {sum v, min positive v, max v}
 // per (CTA, batch).  Pass 2 (mind_fast_fix_kernel) reduces them to mean_all(v) in every CTA and recomputes exactly the
@@ -206,6 +215,26 @@ __device__ __forceinline__ void st4p(float *p, u64 a, u64 b)
     *reinterpret_cast<float4 *>(p) = f;
 }
 
+// S1 task index within a plane -> (halo row, position quad).  LDG modes: row-major, 9 quads per row.  TMA mode (10 quads
+// per row, 20 rows): groups of 40 tasks = 4 rows; the first 32 are quads 0-7 of the four rows, the last 8 are quads 8-9.
+// A 128-bit shared-memory access is served 8 lanes at a time; with this order every 8-lane group reads one row's
+// consecutive chunks (conflict-free in the ws planes AND the 48-column image tiles), except the quad-8/9 group, which is
+// conflict-free in ws (row pitch 10 chunks) and 2-way in the image tiles.  Row-major order made most image-tile groups
+// straddle two rows 12 chunks apart (== 4 mod 8): 2-way conflicts on 7 of the 19 loads of every task.
+template <bool TMA_MODE>
+__device__ __forceinline__ void s1_row_quad(int rem, int &r, int &q)
+{
+    if (TMA_MODE) {
+        static_assert(EH % 4 == 0 || !TMA_MODE, "row groups of four");
+        const int g = rem / 40, u = rem - g * 40;
+        if (u < 32) { r = 4 * g + (u >> 3); q = u & 7; }
+        else { r = 4 * g + ((u - 32) >> 1); q = 8 + (u & 1); }
+    } else {
+        constexpr int NQ = Mode<DGTTA_NOISE_NONE>::NQUAD;
+        r = rem / NQ; q = rem - r * NQ;
+    }
+}
+
 // March one CTA over output planes [d0, d1) of patch (h0, w0) of sample b.
 template <int DELTA, int NOISE, bool FIX>
 __device__ __forceinline__ void process(const Params &P, float *smem, float (*red)[C_WARPS], uint64_t *full_bar,
@@ -346,7 +375,8 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         for (int t = tid; t < S1_TASKS; t += NTHREADS) {
             const int pz = t / (EH * NQUAD);
             const int rem = t - pz * (EH * NQUAD);
-            const int r = rem / NQUAD, q = rem - r * NQUAD;
+            int r, q;
+            s1_row_quad<TMA>(rem, r, q);
             if (zb + pz >= z_end) continue;
             if (TMA && (r < rT || r > rB || w0 - CO + 4 * q < 0 || w0 - CO + 4 * q >= W)) continue;   // not an owner (see below)
             const int zc = clampi(zb + pz, 0, D - 1);
@@ -475,7 +505,8 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         for (int s2_t = opaque(tid); s2_t < S2_TASKS; s2_t += NTHREADS) {
         const int s2_pc = s2_t / NQUAD;                  // pz * 12 + c
         const int s2_pz = s2_pc / 12;
-        if (zb + s2_pz < z_end) {
+        const int s2_gw = w0 - CO + 4 * (s2_t - s2_pc * NQUAD);   // first column of the strip
+        if (zb + s2_pz < z_end && !(TMA && (s2_gw < 0 || s2_gw >= W))) {   // (strips outside the volume: never read)
             float *col = ws + slot_of(s2_pz) * WS_PLANE + (s2_pc - s2_pz * 12) * WS_CH + 4 * (s2_t - s2_pc * NQUAD);
             u64 acc[NT][2];   // partial sums of the 5 output rows that input row r contributes to
             u64 x0 = 0ull, x1 = 0ull;
@@ -523,7 +554,8 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
         }
 
         // ================= C: W smoothing, D window, MIND normalisation, store
-        float st_sum = 0.f, st_min = __int_as_float(0x7f800000), st_max = 0.f;
+        float st_sum = 0.f, st_max = 0.f;
+        unsigned st_minu = 0xffffffffu;   // (bits of the smallest positive v) - 1
         if (c_active) {
 #pragma unroll
             for (int ph = 0; ph < PB; ++ph) {
@@ -543,7 +575,9 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                             const float2 f1 = *reinterpret_cast<const float2 *>(wsp + a * WS_CH + 8);
                             v[0] = f0.x; v[1] = f0.y; v[6] = f1.x; v[7] = f1.y;
                             ld4(wsp + a * WS_CH + 4, &v[2]);
-                            // columns outside the volume replicate the first / last column inside (mind.py:22)
+                            // columns outside the volume replicate the first / last column inside (mind.py:22).  (Two code
+                            // copies selected once per CTA — selects only in patches on a W face — ran slower: the doubled
+                            // instruction footprint showed up as run-to-run variance on every CTA.)
                             if (vw == 0) { v[0] = v[2]; v[1] = v[2]; }
                             if (vw + 4 == W) { v[6] = v[5]; v[7] = v[5]; }
                         } else {
@@ -559,7 +593,8 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                         u64 ob = fmul2(pk(v[4], v[5]), G2[2]);
                         oa = ffma2(s1a, G2[1], oa); ob = ffma2(s1b, G2[1], ob);
                         oa = ffma2(s0a, G2[0], oa); ob = ffma2(s0b, G2[0], ob);
-                        // D smoothing: slots ph, ph+1, ph+2, ph+3 (mod 4) hold planes z-4 .. z-1
+                        // D smoothing: slots ph, ph+1, ph+2, ph+3 (mod 4) hold planes z-4 .. z-1.  (The scatter form — four
+                        // running sums updated in place, no register copies — measured 2-4 % slower.)
                         u64 acc0 = fmul2(win[a][0][ph], G2[0]), acc1 = fmul2(win[a][1][ph], G2[0]);
 #pragma unroll
                         for (int t = 1; t < NWIN; ++t) {
@@ -588,7 +623,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                     for (int j = 0; j < 2; ++j) {
                         float x0[2], x1[2], x2[2];
                         unpk(m[0][j], x0[0], x0[1]); unpk(m[1][j], x1[0], x1[1]); unpk(m[2][j], x2[0], x2[1]);
-                        float mn[2], sc2[2];
+                        float mn[2], sc2[2], vv[2];
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             float t = fminf(fminf(x0[e], x1[e]), x2[e]);
@@ -611,12 +646,21 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                                 v = fminf(fmaxf(v, lo), hi);                               // mind.py:158-160
                                 sc2[e] = -1.4426950408889634f * rcp_approx(v);
                             } else {
-                                const bool cnt = stat_lane && emit && valid(2 * j + e);
-                                st_sum += cnt ? v : 0.f;
-                                st_max = fmaxf(st_max, cnt ? v : 0.f);
-                                st_min = fminf(st_min, (cnt && v > 0.f) ? v : __int_as_float(0x7f800000));
-                                // v == 0 <=> all m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
-                                sc2[e] = v > 0.f ? -1.4426950408889634f * rcp_approx(v) : 0.f;
+                                vv[e] = v;
+                                // v == 0 <=> all m_c == 0: 0 * (-log2e / tiny) = -0 -> exp = 1 = exp(-0/lo) for any lo > 0
+                                // (lo == 0 is caught by pass 2, and so is every v below 1e-37: it is < 0.001 mean(v))
+                                sc2[e] = -1.4426950408889634f * rcp_approx(fmaxf(v, 1e-37f));
+                            }
+                        }
+                        if (!FIX) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                // statistics of the clamp decision: v >= 0, so bit order == value order, and bits - 1 sends
+                                // v == 0 to 0xffffffff, out of the minimum over the positive v
+                                const float vm = (stat_lane && emit && valid(2 * j + e)) ? vv[e] : 0.f;
+                                st_sum += vm;
+                                st_max = fmaxf(st_max, vm);
+                                st_minu = min(st_minu, __float_as_uint(vm) - 1u);
                             }
                         }
                         const u64 SCL = pk(sc2[0], sc2[1]);
@@ -646,6 +690,7 @@ __device__ __forceinline__ void process(const Params &P, float *smem, float (*re
                 }
             }
             if (!FIX) {
+                float st_min = st_minu == 0xffffffffu ? __int_as_float(0x7f800000) : __uint_as_float(st_minu + 1u);
                 st_sum = warp_sum(st_sum); st_min = warp_min(st_min); st_max = warp_max(st_max);
                 if (lane == 0) { red[0][warp] = st_sum; red[1][warp] = st_min; red[2][warp] = st_max; }
             }
@@ -694,390 +739,13 @@ __device__ __forceinline__ void decode_cta(const Params &P, int cta, int &b, int
     d1 = min(P.D, d0 + P.chunkD);
 }
 
-// =====================================================================================================================
-// Plane-pipelined variant (round 2): the three stages run CONCURRENTLY on three consecutive planes instead of one after
-// the other on a 4-plane batch.  Interval i (one __syncthreads each) runs S1 on marched plane i, S2 on plane i-1 and C
-// on plane i-2; a warp executes its row of C and (11 of 16 warps) one 32-task slice of S1 or S2, half of those warps
-// in the order S-then-C and the other half C-then-S.  S1 / S2 are bound by shared-memory bandwidth and C by issue
-// slots / latency, so the mix keeps both resources busy at the same time (the batch kernel leaves the FP32 pipe idle
-// during S1 / S2 and the shared-memory pipe idle during C).  Five ws plane slots: C, S2, S1 and two noise boxes in
-// flight (issued two intervals ahead by thread 0 right after the barrier that retires the slot's previous plane — no
-// empty-barriers); the image planes ride on the same full-barrier as the noise box of the marched plane that needs them
-// first.  TMA staging only (W % 4 == 0, 16-byte aligned tensors); everything else keeps mind_fast_kernel.  Statistics
-// units (4 marched planes) are the batch kernel's, so mind_fast_fix_kernel serves both.
-namespace pipe {
 
-#ifdef DGTTA_PIPE_DEBUG
-__device__ unsigned long long g_dbg[1024][4];   // per CTA: smid, start, end (globaltimer ns), clock cycles
+#ifdef DGTTA_CTA_TIMES
+// developer probe (-DDGTTA_CTA_TIMES, tools/dbg_cta_times.py): per-CTA {smid, start, end (globaltimer ns), cycles} of pass 1.
+// It is what showed that patches on a volume face ran 1.25-1.55x longer than interior ones (round 2).
+__device__ unsigned long long g_dbg[1024][4];
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
-
-#ifndef DGTTA_PIPE_NS
-#define DGTTA_PIPE_NS 5
-#endif
-#ifndef DGTTA_PIPE_ROLES
-#define DGTTA_PIPE_ROLES 0
-#endif
-// NS ws plane slots: C, S2, S1 and LEAD = NS - 3 noise boxes in flight (= intervals between a box's issue and its S1)
-template <int DELTA, int NS> struct PGeom {
-    using M = Mode<NOISE_TMA>;
-    static constexpr int LEAD = NS - 3;
-    static constexpr int TR = EH + 2 * DELTA;
-    static constexpr int NIMG = 2 * DELTA + 1 + LEAD;   // live image planes: S1's 2*delta+1 and LEAD more in flight
-    static constexpr int TILE = TR * M::TWD;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(NS * M::WS_PLANE + NIMG * TILE);
-};
-
-// per-warp role: bits 0-1 kind (0 none, 1 S1, 2 S2), bits 2-4 slice, bit 5 S-before-C
-#define R_S1(k, first) (1 | ((k) << 2) | ((first) << 5))
-#define R_S2(k, first) (2 | ((k) << 2) | ((first) << 5))
-__device__ __forceinline__ int role_of(int warp)
-{
-#if DGTTA_PIPE_ROLES == 0
-    // S-first: S1 slices 0-3 (warps 0-3), S2 slices 0-1 (4, 5); C-first: S1 slices 4-6 (6-8), S2 slices 2-3 (9, 10)
-    static constexpr unsigned char t[16] = {R_S1(0, 1), R_S1(1, 1), R_S1(2, 1), R_S1(3, 1), R_S2(0, 1), R_S2(1, 1), R_S1(4, 0), R_S1(5, 0),
-                                     R_S1(6, 0), R_S2(2, 0), R_S2(3, 0), 0, 0, 0, 0, 0};
-#elif DGTTA_PIPE_ROLES == 1
-    // everybody S-first
-    static constexpr unsigned char t[16] = {R_S1(0, 1), R_S1(1, 1), R_S1(2, 1), R_S1(3, 1), R_S2(0, 1), R_S2(1, 1), R_S1(4, 1), R_S1(5, 1),
-                                     R_S1(6, 1), R_S2(2, 1), R_S2(3, 1), 0, 0, 0, 0, 0};
-#elif DGTTA_PIPE_ROLES == 2
-    // everybody C-first
-    static constexpr unsigned char t[16] = {R_S1(0, 0), R_S1(1, 0), R_S1(2, 0), R_S1(3, 0), R_S2(0, 0), R_S2(1, 0), R_S1(4, 0), R_S1(5, 0),
-                                     R_S1(6, 0), R_S2(2, 0), R_S2(3, 0), 0, 0, 0, 0, 0};
-#else
-    // S2 (the longer task) first on four warps, S1 after C on seven
-    static constexpr unsigned char t[16] = {R_S2(0, 1), R_S2(1, 1), R_S2(2, 1), R_S2(3, 1), R_S1(0, 0), R_S1(1, 0), R_S1(2, 0), R_S1(3, 0),
-                                     R_S1(4, 0), R_S1(5, 0), R_S1(6, 0), 0, 0, 0, 0, 0};
-#endif
-    return t[warp];
-}
-
-template <int DELTA, bool HAS_NOISE, int NS>
-__global__ void __launch_bounds__(512, 1) mind_pipe_kernel(const __grid_constant__ Params P)
-{
-    static_assert(TH == 16, "the pipelined kernel is written for the 16-row patch");
-    static_assert(NS >= 4, "C, S2, S1 and at least one box in flight");
-    using G = PGeom<DELTA, NS>;
-    constexpr int LEAD = G::LEAD;
-    using M = Mode<NOISE_TMA>;
-    constexpr int CO = M::CO, NQUAD = M::NQUAD, TWD = M::TWD, WSP = M::WSP, WS_CH = M::WS_CH, WS_PLANE = M::WS_PLANE;
-    constexpr int S1_PLANE_TASKS = EH * NQUAD, S2_PLANE_TASKS = 12 * NQUAD;   // 200 / 120
-    extern __shared__ __align__(128) float smem[];
-    __shared__ float red[3][C_WARPS];
-    __shared__ uint64_t full_bar[NS];
-    int b, h0, w0, d0, d1;
-    decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
-    float4 *stats = P.stats + (size_t)blockIdx.x * P.nbatch;
-#ifdef DGTTA_PIPE_DEBUG
-    const unsigned long long dbg_t0 = gtimer();
-    const long long dbg_c0 = clock64();
-#endif
-
-    float *ws = smem;
-    float *tiles = smem + NS * WS_PLANE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = P.D, H = P.H, W = P.W, HW = H * W;
-
-    u64 G2[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) G2[t] = pk(P.taps[t], P.taps[t]);
-
-    const int z_begin = d0 - R, z_end = d1 + R;
-    const int NP = z_end - z_begin;               // marched planes
-    const int nb = (NP + PB - 1) / PB;            // statistics units
-
-    // ---- TMA producer (thread 0): marched plane g -> ws slot g % NS; its image planes on the same barrier
-    int loaded_hi = max(clampi(z_begin, 0, D - 1) - DELTA, 0) - 1;
-    auto issue = [&](int g) {
-        const int zc = clampi(z_begin + g, 0, D - 1);
-        const int need_hi = min(zc + DELTA, D - 1);
-        const int np = max(need_hi - loaded_hi, 0);
-        const int s = g % NS;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses of the slot before the async write
-        const unsigned bytes = (unsigned)((HAS_NOISE ? WS_PLANE : 0) + np * G::TILE) * (unsigned)sizeof(float);
-        if (bytes == 0) mbar_arrive(&full_bar[s]);
-        else mbar_expect_tx(&full_bar[s], bytes);
-        for (int q = loaded_hi + 1; q <= need_hi; ++q)
-            tma_load_3d(tiles + (q % G::NIMG) * G::TILE, &P.img_map, &full_bar[s], w0 - CO - 4, h0 - R - DELTA, b * D + q);
-        loaded_hi = max(loaded_hi, need_hi);
-        if (HAS_NOISE) tma_load_4d(ws + s * WS_PLANE, &P.noise_map, &full_bar[s], w0 - CO, h0 - R, zc, b * 12);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int g = 0; g <= LEAD && g < NP; ++g) issue(g);
-    }
-
-    // ---- roles
-    const int role = role_of(warp);
-    const int s_kind = role & 3;
-    const bool s_first = (role >> 5) & 1;
-    const int s_task = ((role >> 2) & 7) * 32 + lane;
-
-    // halo rows / columns outside the volume replicate E^2 of the clamped position (mind.py:22)
-    const int rT = max(0, R - h0), rB = min(EH - 1, H - 1 - h0 + R);
-    const bool scaled = P.in_scale != nullptr;
-    const u64 RW = pk(P.rw, P.rw);
-
-    // ---- C bookkeeping: warp = patch row, lane = (4-column group wl, channel group cg)
-    const int wl = lane & 7, cg = lane >> 3;
-    const int c_off = (3 * cg) * WS_CH + warp * WSP + 4 * wl;
-    const int vh = h0 + warp, vw = w0 + 4 * wl;
-    const bool row_ok = vh < H;
-    auto valid = [&](int k) { return row_ok && vw + k < W; };
-    float *op = P.out + (((size_t)b * 12 + 3 * cg) * D + d0) * HW + (size_t)vh * W + vw;
-    const size_t ch_stride = (size_t)D * HW;
-    const bool vec_store = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && valid(3);   // W % 4 == 0 here
-    const bool stat_lane = cg == 0;
-
-    u64 win[3][2][NWIN];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int t = 0; t < NWIN; ++t) win[a][j][t] = 0ull;
-    float st_sum = 0.f, st_min = __int_as_float(0x7f800000), st_max = 0.f;
-
-    // ================= S1: squared edges of 4 positions x 12 channels (marched plane g)
-    auto s1_task = [&](int g) {
-        const int t = opaque(s_task);
-        if (t >= S1_PLANE_TASKS) return;
-        const int r = t / NQUAD, q = t - r * NQUAD;
-        const int gw0 = w0 - CO + 4 * q;
-        if (r < rT || r > rB || gw0 < 0 || gw0 >= W) return;   // not an owner: the owner of the clamped position writes this quad
-        const int zc = clampi(z_begin + g, 0, D - 1);
-        const int sl = g % NS;
-        const int toff = (r + DELTA) * TWD + 4 + 4 * q;
-        const float *tc = tiles + (zc % G::NIMG) * G::TILE + toff;
-        const float *tm = tiles + (max(zc - DELTA, 0) % G::NIMG) * G::TILE + toff;
-        const float *tp = tiles + (min(zc + DELTA, D - 1) % G::NIMG) * G::TILE + toff;
-        // image tiles arrive with zeros outside the volume: read the clamped row instead (replicate padding,
-        // mind.py:137); tile row i is h = h0 - R - DELTA + i
-        const int row_lo = max(0, R + DELTA - h0), row_hi = min(G::TR - 1, H - 1 - h0 + R + DELTA);
-        const int hm_off = (max(r, row_lo) - (r + DELTA)) * TWD;
-        const int hp_off = (min(r + 2 * DELTA, row_hi) - (r + DELTA)) * TWD;
-        mbar_wait(&full_bar[sl], (unsigned)(g / NS) & 1u);   // noise box of plane g and the newest image plane it needs
-        u64 nbv[6][2];
-        ld4p(tm, nbv[NB_DM][0], nbv[NB_DM][1]);
-        ld4p(tp, nbv[NB_DP][0], nbv[NB_DP][1]);
-        ld4p(tc + hm_off, nbv[NB_HM][0], nbv[NB_HM][1]);
-        ld4p(tc + hp_off, nbv[NB_HP][0], nbv[NB_HP][1]);
-        float wr[12];
-        ld4(tc - 4, &wr[0]); ld4(tc, &wr[4]); ld4(tc + 4, &wr[8]);
-        float wm[4], wp[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { wm[k] = wr[4 + k - DELTA]; wp[k] = wr[4 + k + DELTA]; }
-        if (gw0 == 0) {
-#pragma unroll
-            for (int k = 0; k < DELTA; ++k) wm[k] = wr[4];
-        }
-        if (gw0 + 4 == W) {
-#pragma unroll
-            for (int k = 4 - DELTA; k < 4; ++k) wp[k] = wr[7];
-        }
-        nbv[NB_WM][0] = pk(wm[0], wm[1]); nbv[NB_WM][1] = pk(wm[2], wm[3]);
-        nbv[NB_WP][0] = pk(wp[0], wp[1]); nbv[NB_WP][1] = pk(wp[2], wp[3]);
-        if (scaled) {
-            const float sa = __ldg(P.in_scale + 2 * b), sc = __ldg(P.in_scale + 2 * b + 1);
-            const u64 SA = pk(sa, sa), SC = pk(sc, sc);
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) nbv[a][j] = fmul2(fmul2(nbv[a][j], SA), SC);
-        }
-        float *wsp = ws + sl * WS_PLANE + r * WSP + 4 * q;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            u64 e0 = fsub2(nbv[mind_p1(c)][0], nbv[mind_p2(c)][0]);
-            u64 e1 = fsub2(nbv[mind_p1(c)][1], nbv[mind_p2(c)][1]);
-            if (HAS_NOISE) {
-                u64 n0, n1;
-                ld4p(wsp + c * WS_CH, n0, n1);
-                e0 = fadd2(e0, fmul2(RW, n0));   // product and sum rounded separately, like the reference
-                e1 = fadd2(e1, fmul2(RW, n1));
-            }
-            st4p(wsp + c * WS_CH, fmul2(e0, e0), fmul2(e1, e1));
-        }
-    };
-
-    // ================= S2: H smoothing of one (channel, 4-column strip) of marched plane g, in place
-    auto s2_task = [&](int g) {
-        const int t = opaque(s_task);
-        if (t >= S2_PLANE_TASKS) return;
-        const int c = t / NQUAD;
-        float *col = ws + (g % NS) * WS_PLANE + c * WS_CH + 4 * (t - c * NQUAD);
-        u64 acc[NT][2];
-        u64 x0 = 0ull, x1 = 0ull;
-#pragma unroll
-        for (int r = 0; r < EH; ++r) {
-            // rows outside the volume replicate the first / last row inside (mind.py:22): rows < rT read row rT (rT <= R),
-            // rows > rB keep the registers of row rB
-            if (r < R) ld4p(col + max(r, rT) * WSP, x0, x1);
-            else if (r <= rB) ld4p(col + r * WSP, x0, x1);
-#pragma unroll
-            for (int tt = 0; tt < NT; ++tt) {
-                const int o = r - tt;
-                if (o < 0 || o >= TH) continue;
-                if (tt == 0) { acc[o % NT][0] = fmul2(x0, G2[0]); acc[o % NT][1] = fmul2(x1, G2[0]); }
-                else { acc[o % NT][0] = ffma2(x0, G2[tt], acc[o % NT][0]); acc[o % NT][1] = ffma2(x1, G2[tt], acc[o % NT][1]); }
-            }
-            const int done = r - (NT - 1);
-            if (done >= 0) st4p(col + done * WSP, acc[done % NT][0], acc[done % NT][1]);
-        }
-    };
-
-    // ================= C: W smoothing, D window (slot PH is the oldest plane), MIND normalisation, store
-    auto c_plane = [&](auto PHC, int gc) {
-        constexpr int ph = decltype(PHC)::value;
-        const float *wsp = ws + (gc % NS) * WS_PLANE + c_off;
-        const bool emit = gc >= 2 * R;   // output plane z - R >= d0
-        u64 m[3][2];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float v[8];
-            const float2 f0 = *reinterpret_cast<const float2 *>(wsp + a * WS_CH + 2);
-            const float2 f1 = *reinterpret_cast<const float2 *>(wsp + a * WS_CH + 8);
-            v[0] = f0.x; v[1] = f0.y; v[6] = f1.x; v[7] = f1.y;
-            ld4(wsp + a * WS_CH + 4, &v[2]);
-            // columns outside the volume replicate the first / last column inside (mind.py:22)
-            if (vw == 0) { v[0] = v[2]; v[1] = v[2]; }
-            if (vw + 4 == W) { v[6] = v[5]; v[7] = v[5]; }
-            const u64 s0a = fadd2(pk(v[0], v[1]), pk(v[4], v[5]));
-            const u64 s0b = fadd2(pk(v[2], v[3]), pk(v[6], v[7]));
-            const u64 s1a = pk(v[1] + v[3], v[2] + v[4]);
-            const u64 s1b = pk(v[3] + v[5], v[4] + v[6]);
-            u64 oa = fmul2(pk(v[2], v[3]), G2[2]);
-            u64 ob = fmul2(pk(v[4], v[5]), G2[2]);
-            oa = ffma2(s1a, G2[1], oa); ob = ffma2(s1b, G2[1], ob);
-            oa = ffma2(s0a, G2[0], oa); ob = ffma2(s0b, G2[0], ob);
-            u64 acc0 = fmul2(win[a][0][ph], G2[0]), acc1 = fmul2(win[a][1][ph], G2[0]);
-#pragma unroll
-            for (int t = 1; t < NWIN; ++t) {
-                acc0 = ffma2(win[a][0][(ph + t) % NWIN], G2[t], acc0);
-                acc1 = ffma2(win[a][1][(ph + t) % NWIN], G2[t], acc1);
-            }
-            m[a][0] = ffma2(oa, G2[NT - 1], acc0);
-            m[a][1] = ffma2(ob, G2[NT - 1], acc1);
-            win[a][0][ph] = oa;
-            win[a][1][ph] = ob;
-        }
-        float o[3][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float x0[2], x1[2], x2[2];
-            unpk(m[0][j], x0[0], x0[1]); unpk(m[1][j], x1[0], x1[1]); unpk(m[2][j], x2[0], x2[1]);
-            float mn[2], sc2[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float t = fminf(fminf(x0[e], x1[e]), x2[e]);
-                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 8));
-                t = fminf(t, __shfl_xor_sync(0xffffffffu, t, 16));
-                mn[e] = t;
-            }
-            const u64 MN = pk(mn[0], mn[1]);
-            const u64 m0 = fsub2(m[0][j], MN), m1 = fsub2(m[1][j], MN), m2 = fsub2(m[2][j], MN);   // mind.py:156
-            const u64 S = fadd2(fadd2(m0, m1), m2);
-            float s[2];
-            unpk(S, s[0], s[1]);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float t = s[e];
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                t += __shfl_xor_sync(0xffffffffu, t, 16);
-                const float v = t * (1.f / 12.f);                                   // mind.py:157
-                const bool cnt = stat_lane && emit && valid(2 * j + e);
-                st_sum += cnt ? v : 0.f;
-                st_max = fmaxf(st_max, cnt ? v : 0.f);
-                st_min = fminf(st_min, (cnt && v > 0.f) ? v : __int_as_float(0x7f800000));
-                // v == 0 <=> all m_c == 0: exp(-0/lo) = 1 for any lo > 0 (lo == 0 is caught by pass 2)
-                sc2[e] = v > 0.f ? -1.4426950408889634f * rcp_approx(v) : 0.f;
-            }
-            const u64 SCL = pk(sc2[0], sc2[1]);
-            float y0[2], y1[2], y2[2];
-            unpk(fmul2(m0, SCL), y0[0], y0[1]); unpk(fmul2(m1, SCL), y1[0], y1[1]); unpk(fmul2(m2, SCL), y2[0], y2[1]);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {                                      // mind.py:161-162
-                o[0][2 * j + e] = ex2_approx(y0[e]);
-                o[1][2 * j + e] = ex2_approx(y1[e]);
-                o[2][2 * j + e] = ex2_approx(y2[e]);
-            }
-        }
-        if (emit) {
-            if (vec_store) {
-                __stcs(reinterpret_cast<float4 *>(op), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
-                __stcs(reinterpret_cast<float4 *>(op + ch_stride), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
-                __stcs(reinterpret_cast<float4 *>(op + 2 * ch_stride), make_float4(o[2][0], o[2][1], o[2][2], o[2][3]));
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (valid(k)) __stcs(op + a * ch_stride + k, o[a][k]);
-            }
-            op += HW;
-        }
-    };
-
-    int pending = -1;   // statistics unit parked in `red`, written by warp 0 after the next barrier
-    auto flush_stats = [&]() {
-        if (pending >= 0 && warp == 0) {
-            float s = lane < C_WARPS ? red[0][lane] : 0.f;
-            float mnv = lane < C_WARPS ? red[1][lane] : __int_as_float(0x7f800000);
-            float mxv = lane < C_WARPS ? red[2][lane] : 0.f;
-            s = warp_sum(s); mnv = warp_min(mnv); mxv = warp_max(mxv);
-            if (lane == 0) stats[pending] = make_float4(s, mnv, mxv, 0.f);
-        }
-        pending = -1;
-    };
-
-    const int NI = NP + 2;
-#pragma unroll 1
-    for (int i = 0; i < NI; ++i) {
-        __syncthreads();   // S1(i-1), S2(i-2), C(i-3) complete
-        if (tid == 0 && i >= 1 && i + LEAD < NP) issue(i + LEAD);   // its slot held plane i + LEAD - NS, retired by C in interval i - 1
-        flush_stats();
-        const int gc = i - 2;
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-            if ((sub == 0) == s_first) {
-                if (s_kind == 1) { if (i < NP) s1_task(i); }
-                else if (s_kind == 2) { if (i >= 1 && i - 1 < NP) s2_task(i - 1); }
-            } else if (gc >= 0) {
-                switch (gc & 3) {
-                    case 0: c_plane(std::integral_constant<int, 0>{}, gc); break;
-                    case 1: c_plane(std::integral_constant<int, 1>{}, gc); break;
-                    case 2: c_plane(std::integral_constant<int, 2>{}, gc); break;
-                    default: c_plane(std::integral_constant<int, 3>{}, gc); break;
-                }
-                if ((gc & 3) == 3 || gc == NP - 1) {
-                    st_sum = warp_sum(st_sum); st_min = warp_min(st_min); st_max = warp_max(st_max);
-                    if (lane == 0) { red[0][warp] = st_sum; red[1][warp] = st_min; red[2][warp] = st_max; }
-                    st_sum = 0.f; st_min = __int_as_float(0x7f800000); st_max = 0.f;
-                }
-            }
-        }
-        if (gc >= 0 && ((gc & 3) == 3 || gc == NP - 1)) pending = gc >> 2;
-    }
-    __syncthreads();
-#ifdef DGTTA_PIPE_DEBUG
-    if (tid == 0 && blockIdx.x < 1024) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        g_dbg[blockIdx.x][0] = smid; g_dbg[blockIdx.x][1] = dbg_t0; g_dbg[blockIdx.x][2] = gtimer();
-        g_dbg[blockIdx.x][3] = (unsigned long long)(clock64() - dbg_c0);
-    }
-#endif
-    flush_stats();
-    if (warp == 0)   // units this (shorter) chunk never ran: neutral entries
-        for (int i = nb + lane; i < P.nbatch; i += 32) stats[i] = make_float4(0.f, __int_as_float(0x7f800000), 0.f, 0.f);
-}
-#undef R_S1
-#undef R_S2
-
-}  // namespace pipe
 
 template <int DELTA, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const __grid_constant__ Params P)
@@ -1089,18 +757,18 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mind_fast_kernel(const 
     __shared__ uint64_t img_bar;
     int b, h0, w0, d0, d1;
     decode_cta(P, blockIdx.x, b, h0, w0, d0, d1);
-#if defined(DGTTA_PIPE_DEBUG) && DGTTA_FAST_TH == 16
-    const unsigned long long dbg_t0 = pipe::gtimer();
+#ifdef DGTTA_CTA_TIMES
+    const unsigned long long dbg_t0 = gtimer();
     const long long dbg_c0 = clock64();
 #endif
     process<DELTA, NOISE, false>(P, smem, red, full_bar, empty_bar, &img_bar, b, h0, w0, d0, d1, 0.f, 0.f,
                                  P.stats + (size_t)blockIdx.x * P.nbatch);
-#if defined(DGTTA_PIPE_DEBUG) && DGTTA_FAST_TH == 16
+#ifdef DGTTA_CTA_TIMES
     if (threadIdx.x == 0 && blockIdx.x < 1024) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        pipe::g_dbg[blockIdx.x][0] = smid; pipe::g_dbg[blockIdx.x][1] = dbg_t0; pipe::g_dbg[blockIdx.x][2] = pipe::gtimer();
-        pipe::g_dbg[blockIdx.x][3] = (unsigned long long)(clock64() - dbg_c0);
+        g_dbg[blockIdx.x][0] = smid; g_dbg[blockIdx.x][1] = dbg_t0; g_dbg[blockIdx.x][2] = gtimer();
+        g_dbg[blockIdx.x][3] = (unsigned long long)(clock64() - dbg_c0);
     }
 #endif
 }
@@ -1261,7 +929,7 @@ static CUtensorMapL2promotion l2_promotion()
 // 4-D view (W, H, D, B*12) of the [B,12,D,H,W] noise tensor; box = one halo tile of all 12 channels of one plane
 static bool make_noise_map(Params &P)
 {
-    if ((P.W & 3) || (reinterpret_cast<uintptr_t>(P.noise) & 15)) return false;
+    if ((P.W & 3) || (reinterpret_cast<uintptr_t>(P.noise) & 15) || (reinterpret_cast<uintptr_t>(P.out) & 15)) return false;
     if (getenv("DGTTA_MIND_NO_TMA")) return false;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
@@ -1290,52 +958,9 @@ static bool make_img_map(Params &P)
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// plane-pipelined pass 1 + the batch kernel's fix-up pass (FIXNOISE: the noise mode the fix-up kernel stages with)
-template <int DELTA, bool HAS_NOISE, int FIXNOISE>
-static int launch_pipe(const Params &P0, const Plan &plan, void *workspace, cudaStream_t stream)
-{
-    constexpr int NS = DELTA == 1 ? DGTTA_PIPE_NS : 4;   // shared-memory budget: 5 slots only fit with delta == 1
-    using PG = pipe::PGeom<DELTA, NS>;
-    using G = Geom<DELTA, FIXNOISE>;
-    static_assert(PG::SMEM <= 227 * 1024 - 512, "pipelined MIND kernel: shared-memory budget");
-    static std::atomic<bool> configured_on[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    std::atomic<bool> &configured = configured_on[dev];
-    if (!configured) {
-        cudaFuncSetAttribute(pipe::mind_pipe_kernel<DELTA, HAS_NOISE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG::SMEM);
-        cudaFuncSetAttribute(mind_fast_fix_kernel<DELTA, FIXNOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-        configured = true;
-    }
-    Params P = P0;
-    const int nunits = plan.ncta * plan.nbatch;
-    char *base = (char *)workspace;
-    P.stats = (float4 *)base;
-    int *hdr = (int *)(base + align16((size_t)nunits * sizeof(float4)));
-    float *lohi = (float *)((char *)hdr + align16((size_t)(nunits + 1) * sizeof(int)));
-    P.fix_hdr = hdr;
-    P.fix_lohi = lohi;
-    pipe::mind_pipe_kernel<DELTA, HAS_NOISE, NS><<<plan.ncta, 512, PG::SMEM, stream>>>(P);
-    int rc = check_launch("mind_pipe_kernel");
-    if (rc) return rc;
-    mind_fast_fix_kernel<DELTA, FIXNOISE><<<sm_count() * CTAS_PER_SM, NTHREADS, G::SMEM, stream>>>(
-        P, nunits, 1.0 / ((double)P.B * P.D * P.H * P.W));
-    return check_launch("mind_fast_fix_kernel");
-}
-
-// developer knob: DGTTA_MIND_NO_PIPE=1 keeps the 4-plane batch kernel (A/B timing, bitwise cross-check in the tests)
-static bool pipe_enabled() { return TH == 16 && getenv("DGTTA_MIND_NO_PIPE") == nullptr; }
-
 template <int DELTA>
 static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_mode, cudaStream_t stream)
 {
-    if (pipe_enabled() && getenv("DGTTA_MIND_NO_TMA") == nullptr && (P.W & 3) == 0) {
-        if (noise_mode == DGTTA_NOISE_TENSOR) {
-            if (make_noise_map(P) && make_img_map<DELTA>(P)) return launch_pipe<DELTA, true, NOISE_TMA>(P, plan, workspace, stream);
-        } else if (make_img_map<DELTA>(P)) {
-            return launch_pipe<DELTA, false, DGTTA_NOISE_NONE>(P, plan, workspace, stream);
-        }
-    }
     if (noise_mode == DGTTA_NOISE_TENSOR) {
         constexpr int TMA_MAX_DELTA = CTAS_PER_SM == 1 ? 3 : 1;   // shared-memory budget
         if (DELTA <= TMA_MAX_DELTA && make_noise_map(P) && make_img_map<DELTA <= TMA_MAX_DELTA ? DELTA : 1>(P))
@@ -1347,10 +972,11 @@ static int launch_noise(Params &P, const Plan &plan, void *workspace, int noise_
 
 }  // namespace fast
 
-#ifdef DGTTA_PIPE_DEBUG
-extern "C" int dgtta_debug_pipe_times(unsigned long long *host_out, int n)
+
+#ifdef DGTTA_CTA_TIMES
+extern "C" int dgtta_debug_cta_times(unsigned long long *host_out, int n)
 {
-    return (int)cudaMemcpyFromSymbol(host_out, fast::pipe::g_dbg, sizeof(unsigned long long) * 4 * (n < 1024 ? n : 1024));
+    return (int)cudaMemcpyFromSymbol(host_out, fast::g_dbg, sizeof(unsigned long long) * 4 * (n < 1024 ? n : 1024));
 }
 #endif
 
@@ -1366,9 +992,6 @@ void preload_mind_fast()
     touch_fast<1, DGTTA_NOISE_NONE>(); touch_fast<2, DGTTA_NOISE_NONE>(); touch_fast<3, DGTTA_NOISE_NONE>();
     touch_fast<1, DGTTA_NOISE_TENSOR>(); touch_fast<2, DGTTA_NOISE_TENSOR>(); touch_fast<3, DGTTA_NOISE_TENSOR>();
     touch_fast<1, fast::NOISE_TMA>();
-    DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<1, true, DGTTA_PIPE_NS>); DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<1, false, DGTTA_PIPE_NS>);
-    DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<2, true, 4>); DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<2, false, 4>);
-    DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<3, true, 4>); DGTTA_TOUCH(fast::pipe::mind_pipe_kernel<3, false, 4>);
     if (fast::CTAS_PER_SM == 1) { touch_fast<fast::CTAS_PER_SM == 1 ? 2 : 1, fast::NOISE_TMA>(); touch_fast<fast::CTAS_PER_SM == 1 ? 3 : 1, fast::NOISE_TMA>(); }
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Developer probe (needs a -DDGTTA_PIPE_DEBUG build selected with DGTTA_LIB_PATH): per-CTA start / end times of the
-plane-pipelined MIND kernel."""
+"""Developer probe (needs a -DDGTTA_CTA_TIMES build (tools/build_variant.sh times -DDGTTA_CTA_TIMES) selected with DGTTA_LIB_PATH): per-CTA start / end times of the
+MIND pass-1 kernel (mind_fast_kernel)."""
 import ctypes
 import sys
 from pathlib import Path
@@ -22,8 +22,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 lib = ctypes.CDLL(str(_lib.LIB_PATH))
 buf = np.zeros((1024, 4), dtype=np.uint64)
-lib.dgtta_debug_pipe_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
-rc = lib.dgtta_debug_pipe_times(buf.ctypes.data, 1024)
+lib.dgtta_debug_cta_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
+rc = lib.dgtta_debug_cta_times(buf.ctypes.data, 1024)
 ncta = int((buf[:, 1] > 0).sum())
 b = buf[:ncta].astype(np.int64)
 t0 = b[:, 1].min()
