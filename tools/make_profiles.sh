@@ -33,5 +33,5 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test
     "tests/test_gin_gpu.py::test_single_block_forward" tests/test_host_pipeline_gpu.py -m gpu -q -x > gpurun_out/${tag}_sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_sanitizer_memcheck.log
 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/${tag}_sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/${tag}_sanitizer_racecheck.log
 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/${tag}_sanitizer_memcheck_small.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_sanitizer_memcheck_small.log
-tail -3 gpurun_out/${tag}_sanitizer_*.log
+for f in gpurun_out/${tag}_sanitizer_*.log; do tail -n 3 $f; done
 ls -la gpurun_out | tail -30
