@@ -82,6 +82,8 @@ struct SegParams {
     const float *alphas;   // [B]
     int D, H, W;
     int nTH, nTW, nCD, chunkD;
+    int nb;                // samples in this launch (stack kernels: 1-D grid of nTH * nTW * nb * nCD CTAs, chunk index slowest)
+    int nLong, lenLong, lenShort;   // D chunks: the first nLong of a column have lenLong planes, the others lenShort (see gin_fused_launch)
     int rc, oc;            // channels of in / out per sample
     int n_pro, n_mid, n_epi;
     int b0;                // first sample of this launch
@@ -108,7 +110,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Tail of a last segment: the CTA adds its two sums of squares to a slot of the sample's partials; the CTA that finds
 // it was the sample's last one reduces the slots (fixed order) and writes the re-normalisation factors of gin.py:200-228,
 // scale[b] = {1 / (||mixed_b||_F + 1e-5), ||x_b||_F} — no separate reduction launch.
-__device__ __forceinline__ void finish_norms(const SegParams &P, int b, double s_in, double s_mix, double (*red)[NTHR / 32], int nthr)
+__device__ __forceinline__ void finish_norms(const SegParams &P, int b, double s_in, double s_mix, double (*red)[NTHR / 32], int nthr,
+                                             unsigned cta_in_sample, unsigned ctas_per_sample)
 {
     __shared__ int is_last;
     const int tid = threadIdx.x;
@@ -119,11 +122,11 @@ __device__ __forceinline__ void finish_norms(const SegParams &P, int b, double s
     if (tid == 0) {
         double a = 0.0, m = 0.0;
         for (int i = 0; i < nthr / 32; ++i) { a += red[0][i]; m += red[1][i]; }
-        const int slot = blockIdx.x % RED_SLOTS;
+        const int slot = cta_in_sample % RED_SLOTS;
         atomicAdd(&part[2 * slot], a);
         atomicAdd(&part[2 * slot + 1], m);
         __threadfence();
-        is_last = atomicAdd(&P.counters[b], 1u) == gridDim.x - 1;
+        is_last = atomicAdd(&P.counters[b], 1u) == ctas_per_sample - 1;
     }
     __syncthreads();
     if (!is_last) return;
@@ -256,6 +259,12 @@ __device__ __forceinline__ void finish(const u64 (&a)[4], float (&y)[2][4])
     }
 }
 
+#ifdef DGTTA_CTA_TIMES
+// developer probe (see mind_fast.cu): per-CTA {smid, start, end (globaltimer ns), cycles} of the last gin_stack_kernel launch
+__device__ unsigned long long g_dbg[2048][4];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 // CIN: channels of the tile the segment's first conv reads (after the pro layers).  COUT: channels conv B produces.
 // The mid tile always has two channels (INTERM_CHANNELS).
 template <int CIN, int COUT, bool DOUBLE, bool LAST>
@@ -274,17 +283,24 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
     float (*tmid)[MID_WORDS] = reinterpret_cast<float (*)[MID_WORDS]>(smem_dyn + 2 * IN_WORDS);
     __shared__ double red[2][NTHR / 32];
     const int tid = threadIdx.x;
+#ifdef DGTTA_CTA_TIMES
+    const unsigned long long dbg_t0 = gtimer();
+    const long long dbg_c0 = clock64();
+#endif
     const int D = P.D, H = P.H, W = P.W;
     const size_t HW = (size_t)H * W, V = (size_t)D * HW;
-    const int bl = blockIdx.y;                                 // sample within this launch
+    // 1-D grid, chunk index slowest: the CTAs of chunk 0 (all patches, all samples) launch first, then chunk 1, ...
+    const int npatch = P.nTH * P.nTW;
+    int bid = blockIdx.x;
+    const int patch = bid % npatch; bid /= npatch;
+    const int bl = bid % P.nb;                                 // sample within this launch
+    const int cd = bid / P.nb;
     const int b = P.b0 + bl;
     const SampleWeights &S = P.s[bl];
-    int bid = blockIdx.x;
-    const int cd = bid % P.nCD; bid /= P.nCD;
-    const int tw = bid % P.nTW; bid /= P.nTW;
-    const int th = bid;
+    const int tw = patch % P.nTW, th = patch / P.nTW;
     const int h0 = th * TH, w0 = tw * TW;
-    const int d0 = cd * P.chunkD, d1 = min(D, d0 + P.chunkD);
+    const int d0 = cd < P.nLong ? cd * P.lenLong : P.nLong * P.lenLong + (cd - P.nLong) * P.lenShort;
+    const int d1 = min(D, d0 + (cd < P.nLong ? P.lenLong : P.lenShort));
     const float *in = P.in + (size_t)b * P.rc * V;
 
     // ---- conv-B task of this thread: output row ty, columns w0 + 4 tx ..
@@ -473,7 +489,18 @@ __global__ void __launch_bounds__(NTHR, 2) gin_stack_kernel(const __grid_constan
             rotate(accB);
         }
     }
-    if (LAST) finish_norms(P, b, s_in, s_mix, red, NTHR);
+#ifdef DGTTA_CTA_TIMES
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned lin = blockIdx.x;
+        if (lin < 2048) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_dbg[lin][0] = smid; g_dbg[lin][1] = dbg_t0; g_dbg[lin][2] = gtimer(); g_dbg[lin][3] = (unsigned long long)(clock64() - dbg_c0);
+        }
+    }
+#endif
+    if (LAST) finish_norms(P, b, s_in, s_mix, red, NTHR, (unsigned)(cd * npatch + patch), (unsigned)(npatch * P.nCD));
 }
 
 // stack without any 3x3x3 layer: one elementwise pass over all samples (the four pointwise layers are epi[0..2], pro[0])
@@ -498,7 +525,7 @@ __global__ void __launch_bounds__(256) gin_pointwise_kernel(const __grid_constan
         s_in += (double)x * x; s_mix += (double)c0 * c0;
         out[i] = c0;
     }
-    finish_norms(P, b, s_in, s_mix, red, 256);
+    finish_norms(P, b, s_in, s_mix, red, 256, blockIdx.x, gridDim.x);
 }
 
 static void fill_pointwise(Pointwise &L, const float *ker, const float *shift, int cin, int cout, int act)
@@ -536,6 +563,14 @@ constexpr size_t smem_bytes()
                                     2 * (DOUBLE ? RA * PITCH2 * 2 : 4));
 }
 
+// developer knob: DGTTA_GIN_SKEW = ratio long / short chunk (planes incl. warm-up); 1 disables the skew
+static double gin_chunk_skew()
+{
+    const char *e = getenv("DGTTA_GIN_SKEW");
+    const double v = e ? atof(e) : 1.5;
+    return v >= 1.0 && v <= 4.0 ? v : 1.5;
+}
+
 template <int CIN, int COUT, bool DOUBLE, bool LAST>
 static void launch_one(const SegParams &P, dim3 grid, cudaStream_t stream)
 {
@@ -568,6 +603,13 @@ static void touch_variant()
 }
 
 }  // namespace gins
+
+#ifdef DGTTA_CTA_TIMES
+extern "C" int dgtta_debug_gin_cta_times(unsigned long long *host_out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host_out, gins::g_dbg, sizeof(unsigned long long) * 4 * (n < 2048 ? n : 2048));
+}
+#endif
 
 void preload_gin_fused()
 {
@@ -677,7 +719,27 @@ int gin_fused_launch(const float *x_dev, float *out_dev, const float *params_hos
             }
             P.chunkD = (D + ncd - 1) / ncd;
             P.nCD = (D + P.chunkD - 1) / P.chunkD;
-            const dim3 grid((unsigned)(P.nTH * P.nTW * P.nCD), (unsigned)nb);
+            P.nb = nb;
+            P.nLong = P.nCD; P.lenLong = P.chunkD; P.lenShort = P.chunkD;
+            // Long and short chunks.  When the whole launch is ONE wave with two CTAs on (nearly) every SM, the CTA that
+            // got its SM first runs ~1.5x faster than the one that joined it (measured with the per-CTA timing probe:
+            // 145 vs 190 us for the same 53 planes; the warp schedulers favour the older CTA), and the slower one then
+            // finishes alone at half the SM's throughput.  The CTAs of the first half of the launch order therefore get
+            // chunks that are GIN_SKEW times longer (warm-up planes included) so that both CTAs of an SM end together.
+            // Only the timing depends on this guess about the block scheduler, never the result.
+            {
+                const long ctas = base * P.nCD;
+                const double skew = gin_chunk_skew();
+                if (skew > 1.0 && P.nCD >= 2 && (P.nCD & 1) == 0 && ctas <= slots && ctas > sm_count() + sm_count() / 2) {
+                    const int half = P.nCD / 2;
+                    int S_ = (int)(((double)D / half - (skew - 1.0) * warm) / (1.0 + skew));
+                    if (S_ >= 8) {
+                        const int L_ = (D - half * S_ + half - 1) / half;
+                        P.nLong = half; P.lenLong = L_; P.lenShort = S_;
+                    }
+                }
+            }
+            const dim3 grid((unsigned)(P.nTH * P.nTW * P.nCD * nb));
             const int code = (cin_tile - 1) * 2 + (cout_b - 1);
             if (dbl) {
                 switch (code) {

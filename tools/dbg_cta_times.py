@@ -15,15 +15,32 @@ from dg_tta_b200 import _lib  # noqa: E402
 from gpu_util import synth_volume  # noqa: E402
 
 shape = tuple(int(v) for v in sys.argv[1].split("x")) if len(sys.argv) > 1 else (2, 1, 192, 192, 192)
+what = sys.argv[2] if len(sys.argv) > 2 else "mind"      # "mind" | "gin" (the LAST gin_stack_kernel launch of an all-3x3x3 stack)
 x = synth_volume(shape, 1).cuda()
-n = torch.randn((shape[0], 12) + shape[2:], device="cuda")
-for _ in range(3):
-    mind_ssc(x, noise=n)
-torch.cuda.synchronize()
 lib = ctypes.CDLL(str(_lib.LIB_PATH))
-buf = np.zeros((1024, 4), dtype=np.uint64)
-lib.dgtta_debug_cta_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
-rc = lib.dgtta_debug_cta_times(buf.ctypes.data, 1024)
+buf = np.zeros((2048, 4), dtype=np.uint64)
+if what == "mind":
+    n = torch.randn((shape[0], 12) + shape[2:], device="cuda")
+    for _ in range(3):
+        mind_ssc(x, noise=n)
+    torch.cuda.synchronize()
+    lib.dgtta_debug_cta_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    rc = lib.dgtta_debug_cta_times(buf.ctypes.data, 1024)
+else:
+    from dg_tta_b200.gin import GINGroupConv, gin_forward
+    net = GINGroupConv(dict(IN_CHANNELS=1, N_LAYER=4, INTERM_CHANNELS=2))
+    seed = 0
+    while True:
+        torch.manual_seed(seed)
+        alphas, kers, shifts = net.draw(x)
+        if [k.shape[-1] for k in kers] == [3, 3, 3, 3]:
+            break
+        seed += 1
+    for _ in range(3):
+        gin_forward(x, kers, shifts, alphas, 2)
+    torch.cuda.synchronize()
+    lib.dgtta_debug_gin_cta_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    rc = lib.dgtta_debug_gin_cta_times(buf.ctypes.data, 2048)
 ncta = int((buf[:, 1] > 0).sum())
 b = buf[:ncta].astype(np.int64)
 t0 = b[:, 1].min()
@@ -39,3 +56,19 @@ print("fastest CTAs (cta, smid, dur):", [(int(i), int(b[i, 0]), round(float(dur[
 print("slowest CTAs (cta, smid, dur):", [(int(i), int(b[i, 0]), round(float(dur[i]), 1)) for i in order[-8:]])
 hist, edges = np.histogram(dur, bins=10)
 print("hist", list(zip(np.round(edges[:-1], 0).tolist(), hist.tolist())))
+if what == "gin":
+    # grid.x = nTH * nTW * nCD (cd fastest), grid.y = sample
+    per = {}
+    nx = ncta // shape[0]
+    for i in range(ncta):
+        bid, smp = i % nx, i // nx
+        cd = bid % 4
+        per.setdefault((smp, cd), []).append(float(dur[i]))
+    for k in sorted(per):
+        v = np.array(per[k])
+        print("sample %d chunk %d: n %d  min %.1f med %.1f max %.1f" % (k[0], k[1], len(v), v.min(), np.median(v), v.max()))
+    sm_of = {}
+    for i in range(ncta):
+        sm_of.setdefault(int(b[i, 0]), []).append(i)
+    pairs = [(round(float(dur[v[0]]), 1), round(float(dur[v[1]]), 1), v) for v in sm_of.values() if len(v) == 2][:12]
+    print("co-resident pairs (dur, dur, ctas):", pairs)

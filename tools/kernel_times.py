@@ -30,7 +30,7 @@ def timeit(fn, iters=10, warm=3):
 def main():
     res = {}
     only = sys.argv[1] if len(sys.argv) > 1 else ""   # "mind": MIND timings only
-    for shape in [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]:
+    for shape in ([] if only == "gin" else [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]):
         x = synth_volume(shape, 1).cuda()
         vox = x.numel()
         for delta in (1, 2):
@@ -42,7 +42,7 @@ def main():
         med, best = timeit(lambda: mind_ssc(x))
         res[f"mind_default_randn_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6)
     from dg_tta_b200.mind import randn_like_reference
-    for shape in [(2, 12, 192, 192, 192)]:
+    for shape in ([] if only == "gin" else [(2, 12, 192, 192, 192)]):
         med, best = timeit(lambda: torch.randn(shape, device="cuda"))
         res["torch_randn_2x12x192"] = dict(ms=med, best=best, gbs=2 * 12 * 192 ** 3 * 4 / med / 1e6)
         med, best = timeit(lambda: randn_like_reference(shape, "cuda"))
