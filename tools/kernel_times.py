@@ -30,7 +30,7 @@ def timeit(fn, iters=10, warm=3):
 def main():
     res = {}
     only = sys.argv[1] if len(sys.argv) > 1 else ""   # "mind": MIND timings only
-    for shape in ([] if only == "gin" else [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]):
+    for shape in ([] if only in ("gin", "sampler") else [(1, 1, 128, 128, 128), (2, 1, 192, 192, 192)]):
         x = synth_volume(shape, 1).cuda()
         vox = x.numel()
         for delta in (1, 2):
@@ -42,7 +42,7 @@ def main():
         med, best = timeit(lambda: mind_ssc(x))
         res[f"mind_default_randn_{shape[0]}x{shape[2]}"] = dict(ms=med, best=best, gvox_s=vox / med / 1e6)
     from dg_tta_b200.mind import randn_like_reference
-    for shape in ([] if only == "gin" else [(2, 12, 192, 192, 192)]):
+    for shape in ([] if only in ("gin", "sampler") else [(2, 12, 192, 192, 192)]):
         med, best = timeit(lambda: torch.randn(shape, device="cuda"))
         res["torch_randn_2x12x192"] = dict(ms=med, best=best, gbs=2 * 12 * 192 ** 3 * 4 / med / 1e6)
         med, best = timeit(lambda: randn_like_reference(shape, "cuda"))
@@ -53,7 +53,7 @@ def main():
         return
     x = synth_volume((2, 1, 192, 192, 192), 2).cuda()
     net = GINGroupConv(dict(IN_CHANNELS=1, N_LAYER=4, INTERM_CHANNELS=2))
-    for want in ([1, 1, 1, 1], [3, 3, 3, 3], [3, 1, 3, 1]):
+    for want in ([] if only == "sampler" else [[1, 1, 1, 1], [3, 3, 3, 3], [3, 1, 3, 1]]):
         seed = 0
         while True:
             torch.manual_seed(seed)
@@ -66,17 +66,18 @@ def main():
     # gin_aug over seeds 0..15 (all 16 draws of the four kernel sizes occur with equal probability)
     from dg_tta_b200.gin import gin_aug
     per_seed = []
-    for seed in range(16):
+    for seed in range(0 if only == "sampler" else 16):
         def run(seed=seed):
             torch.manual_seed(seed)
             return gin_aug(x)
         med, _ = timeit(run, iters=5, warm=2)
         per_seed.append(med)
-    res["gin_aug_seeds0_15_2x192"] = dict(ms=sum(per_seed) / 16, best=min(per_seed), worst=max(per_seed),
+    if per_seed:
+      res["gin_aug_seeds0_15_2x192"] = dict(ms=sum(per_seed) / 16, best=min(per_seed), worst=max(per_seed),
                                           gvox_s=x.numel() / (sum(per_seed) / 16) / 1e6)
     # GIN -> MIND on the MultiRes volume / patch shapes
     from dg_tta_b200.tta.augmentation_utils import gin_mind_aug
-    for dhw in [(231, 228, 242), (116, 114, 121), (58, 57, 60), (38, 38, 40), (56, 56, 64), (28, 28, 32), (19, 19, 21)]:
+    for dhw in ([] if only == "sampler" else [(231, 228, 242), (116, 114, 121), (58, 57, 60), (38, 38, 40), (56, 56, 64), (28, 28, 32), (19, 19, 21)]):
         xm = synth_volume((2, 1) + dhw, 4).cuda()
         def run(xm=xm):
             torch.manual_seed(1)
