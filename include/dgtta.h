@@ -134,7 +134,11 @@ int dgtta_gin_layer_fwd(const float *x_dev, float *out_dev, const float *ker_hos
  * and dg_tta/tta/torch_utils.py:55-73 (patch crop; nearest for labels), align_corners=False.
  * No grid tensor exists: coordinates come from theta in-kernel.
  *   in_dev [B,C,Di,Hi,Wi]  theta_dev [B,3,4]  out_dev [B,C,Do,Ho,Wo]
- * bwd_input: grad_in_dev [B,C,Di,Hi,Wi] is overwritten with the adjoint of the trilinear forward.
+ * bwd_input: grad_in_dev [B,C,Di,Hi,Wi] is overwritten with the adjoint of the trilinear forward.  Default: scatter with
+ * red.global.add.f32 like torch's grid_sample backward (summation order, hence the last bits, vary from run to run).
+ * Environment DGTTA_SAMPLE_BWD_DETERMINISTIC=1 (zeros padding): gather over the source voxels instead — every element
+ * written once, bit-identical from run to run, ~2.4x the scatter's time; affines that magnify more than ~2.5x fall
+ * back to the scatter (decided on the device).
  * ------------------------------------------------------------------------------------------- */
 int dgtta_affine_sample_fwd(const float *in_dev, const float *theta_dev, float *out_dev, int B, int C, int Di,
                             int Hi, int Wi, int Do, int Ho, int Wo, int interp, int padding,

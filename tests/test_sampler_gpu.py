@@ -82,6 +82,40 @@ def test_against_oracle_full_patch():
     assert np.abs(s.grad.cpu().numpy() - gref).max() <= 5e-5 * max(1.0, np.abs(gref).max())
 
 
+@pytest.mark.parametrize("kind", ["tta", "shrink", "magnify", "flip"])
+def test_deterministic_gather_backward(kind, monkeypatch):
+    """DGTTA_SAMPLE_BWD_DETERMINISTIC=1: the adjoint as a gather over the source voxels (no atomics).  Same gradient as the
+    scatter up to summation order and as the C oracle's adjoint, bit-identical from run to run; an affine that magnifies
+    strongly makes the candidate boxes large and the call falls back to the scatter on the device (still correct)."""
+    from dg_tta_b200.tta.augmentation_utils import affine_grid_sample, get_rand_affine
+    from oracle import cform
+    torch.manual_seed(11)
+    _, Ri = get_rand_affine(2)
+    if kind == "shrink":      # output covers a sub-region: source voxels outside receive nothing, inside ~(1/0.6)^3 outputs each
+        Ri = Ri.clone(); Ri[:, :, :3] *= 0.6
+    elif kind == "magnify":   # each source voxel is hit by ~(1/3)^-3 = 27x more outputs: candidate box > 6 -> scatter fallback
+        Ri = Ri.clone(); Ri[:, :, :3] *= 3.0
+    elif kind == "flip":
+        Ri = Ri.clone(); Ri[:, 0] *= -1.0
+    lg = synth_volume((2, 5, 33, 40, 52), 41)
+    go = synth_volume((2, 5, 30, 44, 48), 42)
+
+    def grad():
+        s = lg.cuda().requires_grad_(True)
+        (affine_grid_sample(s, Ri, out_size=go.shape[-3:]) * go.cuda()).sum().backward()
+        return s.grad.clone()
+
+    monkeypatch.delenv("DGTTA_SAMPLE_BWD_DETERMINISTIC", raising=False)
+    g_scatter = grad()
+    monkeypatch.setenv("DGTTA_SAMPLE_BWD_DETERMINISTIC", "1")
+    g1, g2 = grad(), grad()
+    assert torch.equal(g1, g2)
+    scale = max(1.0, float(g_scatter.abs().max()))
+    assert float((g1 - g_scatter).abs().max()) <= 2e-5 * scale
+    gref = cform.affine_sample_bwd_input(go.numpy(), Ri.numpy(), lg.shape)
+    assert np.abs(g1.cpu().numpy() - gref).max() <= 5e-5 * max(1.0, np.abs(gref).max())
+
+
 def test_gin_mind_aug_fused_chain():
     from dg_tta_b200.gin import gin_forward
     from dg_tta_b200 import mind_ssc
