@@ -30,7 +30,7 @@ python tests/perf_eager_gpu.py > gpurun_out/${tag}_eager_vs_ours.json 2>> gpurun
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${tag}_nvidia_smi.csv
 # 4. compute-sanitizer over small-shape parity tests of every kernel family (memcheck) and the TMA / mbarrier MIND path (racecheck)
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_boundary_behaviour_gpu.py tests/test_resize_gpu.py tests/test_philox_gpu.py \
-    "tests/test_gin_gpu.py::test_single_block_forward" tests/test_host_pipeline_gpu.py -m gpu -q -x > gpurun_out/${tag}_sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_sanitizer_memcheck.log
+    "tests/test_gin_gpu.py::test_single_block_forward" "tests/test_sampler_gpu.py::test_deterministic_gather_backward" tests/test_host_pipeline_gpu.py -m gpu -q -x > gpurun_out/${tag}_sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_sanitizer_memcheck.log
 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/${tag}_sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/${tag}_sanitizer_racecheck.log
 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/${tag}_sanitizer_memcheck_small.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_sanitizer_memcheck_small.log
 for f in gpurun_out/${tag}_sanitizer_*.log; do tail -n 3 $f; done
