@@ -57,12 +57,13 @@ print("slowest CTAs (cta, smid, dur):", [(int(i), int(b[i, 0]), round(float(dur[
 hist, edges = np.histogram(dur, bins=10)
 print("hist", list(zip(np.round(edges[:-1], 0).tolist(), hist.tolist())))
 if what == "gin":
-    # grid.x = nTH * nTW * nCD (cd fastest), grid.y = sample
+    # 1-D grid, chunk index slowest: lin = cd * (npatch * nb) + sample * npatch + patch; an all-3x3x3 stack on 192^3 has 4 chunks
     per = {}
-    nx = ncta // shape[0]
+    nchunk = 4
+    per_chunk = ncta // nchunk
+    npatch = per_chunk // shape[0]
     for i in range(ncta):
-        bid, smp = i % nx, i // nx
-        cd = bid % 4
+        cd, smp = i // per_chunk, (i % per_chunk) // npatch
         per.setdefault((smp, cd), []).append(float(dur[i]))
     for k in sorted(per):
         v = np.array(per[k])
