@@ -221,6 +221,56 @@ def bind_rank_to_cores(local_rank, world):
         return None
 
 
+def config0_record(dev, peak):
+    """BASELINE.json configs[0]: MIND-SSC (radius 2, dilation 2) on one 1x1x128^3 volume, kernel vs the reference's torch
+    CPU path.  The kernel is timed over 20 calls rotating through 4 input / noise sets (their outputs are fresh 96 MB
+    tensors: the working set of consecutive calls exceeds the 126 MB L2); the CPU number is ONE call of the torch-CPU
+    port on all host cores."""
+    import torch
+    from dg_tta_b200.mind import mind_ssc
+    from oracle import ref_port
+    shape = (1, 1, 128, 128, 128)
+    vox = 128 ** 3
+    xs = [synth_volume(shape, 1000 + i) for i in range(4)]
+    g = torch.Generator().manual_seed(5)
+    ns = [torch.randn((1, 12, 128, 128, 128), generator=g) for _ in range(4)]
+    xd, nd = [x.to(dev) for x in xs], [n.to(dev) for n in ns]
+    for i in range(4):
+        mind_ssc(xd[i], delta=2, noise=nd[i])
+    torch.cuda.synchronize()
+    pairs = []
+    for i in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mind_ssc(xd[i % 4], delta=2, noise=nd[i % 4])
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs)
+    for i in range(2):
+        mind_ssc(xd[i], delta=2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        mind_ssc(xd[i % 4], delta=2)              # reference-default call: Philox field + MIND
+    e1.record()
+    torch.cuda.synchronize()
+    d_ms = e0.elapsed_time(e1) / 20
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_port.mind_ssc(xs[0][:, :, :16].contiguous(), delta=2, noise=ns[0][:, :, :16].contiguous())   # warm-up
+    c0 = time.perf_counter()
+    ref_port.mind_ssc(xs[0], delta=2, noise=ns[0])
+    cpu_ms = (time.perf_counter() - c0) * 1e3
+    gbs = MIND_BYTES_PER_VOXEL_NOISE * vox / (k_ms * 1e-3) / 1e9
+    return {"workload": "MIND-SSC delta=2 sigma=1 randn_weighting=0.05 on 1x1x128x128x128 fp32 (BASELINE.json configs[0])",
+            "kernel_ms": k_ms, "voxels_per_s": vox / (k_ms * 1e-3), "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+            "algorithmic_bytes_per_voxel": MIND_BYTES_PER_VOXEL_NOISE,
+            "default_call_ms": d_ms, "default_call_voxels_per_s": vox / (d_ms * 1e-3),
+            "cpu_reference_ms": cpu_ms, "cpu_reference_voxels_per_s": vox / (cpu_ms * 1e-3), "cpu_cores": torch.get_num_threads(),
+            "cpu_kind": "port (oracle/ref_port.py: the reference's ATen op sequence)"}
+
+
 def gpu_eager_baseline(xs, dev, reps=3):
     """The reference's own op sequence (torch eager: pad/conv3d chains, grouped convs; oracle/ref_port.py issues the same
     ATen ops) on the SAME GPU with TF32 off — the kernel-vs-kernel bar of SURVEY.md §2b / BASELINE.md §4.  A reported
@@ -544,6 +594,12 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     achieved = MIND_BYTES_PER_VOXEL_NOISE * vox_step / (mind_kernel_ms * 1e-3) / 1e9
     traffic = committed_dram_traffic()
+    config0 = None
+    if not os.environ.get("DGTTA_BENCH_NO_CONFIG0"):
+        try:
+            config0 = config0_record(dev, peak)
+        except Exception as exc:   # an extra record must not take the contract line down with it
+            config0 = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
     # CPU baseline: the torch-CPU port on a bounded slab of the same batch (~15 s of CPU work), on ALL host cores (the
     # other ranks have finished; undo this rank's core binding)
@@ -588,6 +644,7 @@ def run_ours(args, rank, world, local_rank):
                         "fixture 12->105 ch (PyTorch/cuDNN, out of scope) -> channel select 14 -> inverse warp -> fused soft-Dice "
                         "consistency -> backward; patch 128^3, batch 2, one 231x228x242 volume per GPU (BASELINE configs[2]/[4])"},
         "gpu_eager_baseline": eager,
+        "config0": config0,
         "gpu_launches": int(launches),   # kernels of libdgtta_sm100.so in the timed region (counted inside the library)
         "roofline": {"bound": "hbm", "kernel": "mind_fast_kernel<delta=1, noise and image tiles staged by TMA> (+finalize, fix-up)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
