@@ -82,7 +82,7 @@ def test_against_oracle_full_patch():
     assert np.abs(s.grad.cpu().numpy() - gref).max() <= 5e-5 * max(1.0, np.abs(gref).max())
 
 
-@pytest.mark.parametrize("kind", ["tta", "shrink", "magnify", "flip"])
+@pytest.mark.parametrize("kind", ["tta", "shrink", "magnify", "flip", "many_channels"])
 def test_deterministic_gather_backward(kind, monkeypatch):
     """DGTTA_SAMPLE_BWD_DETERMINISTIC=1: the adjoint as a gather over the source voxels (no atomics).  Same gradient as the
     scatter up to summation order and as the C oracle's adjoint, bit-identical from run to run; an affine that magnifies
@@ -97,8 +97,9 @@ def test_deterministic_gather_backward(kind, monkeypatch):
         Ri = Ri.clone(); Ri[:, :, :3] *= 3.0
     elif kind == "flip":
         Ri = Ri.clone(); Ri[:, 0] *= -1.0
-    lg = synth_volume((2, 5, 33, 40, 52), 41)
-    go = synth_volume((2, 5, 30, 44, 48), 42)
+    C = 19 if kind == "many_channels" else 5     # more than the 16 channel accumulators of one pass
+    lg = synth_volume((2, C, 33, 40, 52), 41)
+    go = synth_volume((2, C, 30, 44, 48), 42)
 
     def grad():
         s = lg.cuda().requires_grad_(True)
